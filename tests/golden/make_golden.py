@@ -1,0 +1,266 @@
+"""Generate the committed golden vectors by running the UNMODIFIED reference (imported from
+/root/reference/src through oracle/ref_shims).  Runs only in the build container; the outputs
+(tests/golden/*.npz, *.json) are committed and are what tests/ (CPU and GPU) compare against.
+
+    python tests/golden/make_golden.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+import oracle.ref_shims.install as shims  # noqa: E402
+
+shims.install()
+
+from reversi_zero.lib import bitboard as rb  # noqa: E402
+from reversi_zero.env.reversi_env import ReversiEnv, Player, Winner  # noqa: E402
+from reversi_zero.config import Config  # noqa: E402
+from reversi_zero.agent.player import ReversiPlayer  # noqa: E402
+from reversi_zero.lib.util import parse_to_bitboards  # noqa: E402
+
+SEED = 20260922
+U64 = np.uint64
+
+
+def random_positions(rng, n):
+    """SURVEY §8(d) config-5 recipe: densities 1/4, 1/2, 3/4; own/enemy disjoint."""
+    a = rng.integers(0, 2 ** 64, size=n, dtype=U64)
+    b = rng.integers(0, 2 ** 64, size=n, dtype=U64)
+    r = rng.integers(0, 2 ** 64, size=n, dtype=U64)
+    third = n // 3
+    occ = a.copy()
+    occ[:third] = a[:third] & b[:third]
+    occ[2 * third:] = a[2 * third:] | b[2 * third:]
+    own, enemy = occ & r, occ & ~r
+    pos = rng.integers(0, 64, size=n, dtype=np.uint8)
+    return own, enemy, pos
+
+
+def env_state(env):
+    w = 0 if env.winner is None else env.winner.value
+    return [int(env.board.black), int(env.board.white), env.next_player.value, env.turn, int(env.done), w]
+
+
+def gen_bitboard():
+    rng = np.random.default_rng(SEED)
+    own, enemy, pos = random_positions(rng, 3000)
+    # reachable positions from random playouts
+    r_own, r_enemy = [], []
+    for g in range(40):
+        env = ReversiEnv().reset()
+        while not env.done:
+            o, e = env.get_own_and_enemy()
+            r_own.append(o); r_enemy.append(e)
+            legal = rb.find_correct_moves(o, e)
+            moves = [i for i in range(64) if legal >> i & 1]
+            env.step(int(moves[rng.integers(len(moves))]))
+    r_own = np.array(r_own, dtype=U64); r_enemy = np.array(r_enemy, dtype=U64)
+    own = np.concatenate([own, r_own]); enemy = np.concatenate([enemy, r_enemy])
+    pos = np.concatenate([pos, rng.integers(0, 64, size=r_own.size, dtype=np.uint8)])
+    legal = np.array([rb.find_correct_moves(int(o), int(e)) for o, e in zip(own, enemy)], dtype=U64)
+    flip = np.array([rb.calc_flip(int(p), int(o), int(e)) for p, o, e in zip(pos, own, enemy)], dtype=U64)
+    # all 64 squares on a subset (illegal squares included)
+    sub = np.arange(0, own.size, 37)
+    flip_all = np.array([[rb.calc_flip(p, int(own[i]), int(enemy[i])) for p in range(64)] for i in sub], dtype=U64)
+    fv = np.array([rb.flip_vertical(int(x)) for x in own], dtype=U64)
+    fd = np.array([rb.flip_diag_a1h8(int(x)) for x in own], dtype=U64)
+    r90 = np.array([rb.rotate90(int(x)) for x in own], dtype=U64)
+    r180 = np.array([rb.rotate180(int(x)) for x in own], dtype=U64)
+    cnt = np.array([rb.bit_count(int(x)) for x in own], dtype=np.int32)
+    np.savez_compressed(os.path.join(HERE, "bitboard.npz"), own=own, enemy=enemy, pos=pos, legal=legal, flip=flip,
+                        sub=sub, flip_all=flip_all, flip_vertical=fv, flip_diag=fd, rotate90=r90, rotate180=r180,
+                        bit_count=cnt)
+    # reference KATs, test/lib/test_bitboard.py:11-112 (ASCII boards parsed with the reference parser)
+    kats = []
+    boards = {
+        "kat1": "##########\n#OO      #\n#XOO     #\n#OXOOO   #\n#  XOX   #\n#   XXX  #\n#  X     #\n# X      #\n#        #\n##########",
+        "kat2": "##########\n#OOOOOXO #\n#OOOOOXOO#\n#OOOOOXOO#\n#OXOXOXOO#\n#OOXOXOXO#\n#OOOOOOOO#\n#XXXO   O#\n#        #\n##########",
+        "kat3": "##########\n#OOXXXXX #\n#XOXXXXXX#\n#XXXXXXXX#\n#XOOXXXXX#\n#OXXXOOOX#\n#OXXOOOOX#\n#OXXXOOOX#\n# OOOOOOO#\n##########",
+    }
+    for name, s in boards.items():
+        b, w = parse_to_bitboards(s)
+        kats.append(dict(name=name, black=b, white=w, legal_black=rb.find_correct_moves(b, w),
+                         legal_white=rb.find_correct_moves(w, b)))
+    return kats
+
+
+def gen_env():
+    rng = np.random.default_rng(SEED + 1)
+    games = []
+
+    def play(chooser, tag):
+        env = ReversiEnv().reset()
+        actions, states, legals = [], [env_state(env)], []
+        while not env.done:
+            o, e = env.get_own_and_enemy()
+            legal = rb.find_correct_moves(o, e)
+            legals.append(int(legal))
+            a = chooser(legal)
+            actions.append(a)
+            env.step(a)
+            states.append(env_state(env))
+        games.append(dict(tag=tag, actions=actions, states=states, legals=legals))
+
+    play(lambda legal: (legal & -legal).bit_length() - 1, "lowest")
+    play(lambda legal: legal.bit_length() - 1, "highest")
+    for g in range(60):
+        play(lambda legal: int([i for i in range(64) if legal >> i & 1][rng.integers(bin(legal).count("1"))]), f"random{g}")
+    # resign (None) and illegal-move cases, reversi_env.py:49-59
+    special = []
+    for (nm, acts) in (("resign_black", [None]), ("resign_white", [19, None]), ("illegal_black", [0]),
+                       ("illegal_white", [19, 63]), ("occupied", [27])):
+        env = ReversiEnv().reset()
+        sts = [env_state(env)]
+        for a in acts:
+            env.step(a)
+            sts.append(env_state(env))
+        special.append(dict(tag=nm, actions=[-1 if a is None else a for a in acts], states=sts))
+    # update(): turn computation + Board() zero quirk
+    upd = []
+    for b, w, p in ((0x00000000081d0603, 0x0002043814020100, 1), (0x0088ffabd5dfdf5f, 0x000700542a202020, 2), (0, 5, 1)):
+        env = ReversiEnv().update(b, w, Player(p))
+        upd.append(dict(args=[b, w, p], state=env_state(env)))
+    return dict(games=games, special=special, update=upd)
+
+
+def gen_symmetry():
+    rng = np.random.default_rng(SEED + 2)
+    cfg = Config()
+    out = []
+    for i in range(6):
+        own, enemy, _ = random_positions(rng, 3)
+        own, enemy = int(own[i % 3]), int(enemy[i % 3])
+        policy = rng.random(64)
+        policy /= policy.sum()
+        pl = ReversiPlayer(cfg, None, api=object())
+        pl.add_data_to_move_buffer_with_8_symmetries(own, enemy, policy)
+        out.append(dict(own=own, enemy=enemy, policy=list(policy),
+                        records=[[[int(o), int(e)], [float(x) for x in p]] for (o, e), p in pl.moves]))
+    # inverse transform of the NN policy, player.py:300-321, all 8 (flip, rot) combinations
+    inv = []
+    for flip in (False, True):
+        for rot in range(4):
+            bw = 0x00000000081d0603
+            t = bw
+            if flip:
+                t = rb.flip_vertical(t)
+            for _ in range(rot):
+                t = rb.rotate90(t)
+            leaf_p = np.arange(64, dtype=np.float32)  # value = index in the transformed frame
+            lp = leaf_p.reshape(8, 8)
+            if rot > 0:
+                lp = np.rot90(lp, k=rot)
+            if flip:
+                lp = np.flipud(lp)
+            inv.append(dict(flip=int(flip), rot=rot, board=bw, transformed=int(t), src_index=[int(x) for x in lp.reshape(64)]))
+    return dict(records=out, inverse=inv)
+
+
+class FakeNet:
+    """Same function as oracle.nn.FakeNetAPI (kept separate so the golden run depends on nothing of ours)."""
+
+    def __init__(self):
+        self.rows = 0
+
+    def predict(self, x):
+        x = np.asarray(x)
+        n = x.shape[0]
+        self.rows += n
+        p = np.full((n, 64), 1.0 / 64, dtype=np.float32)
+        cnt = x.reshape(n, 2, 64).astype(np.int32).sum(axis=2)
+        v = ((cnt[:, 0] - cnt[:, 1]).astype(np.float32) / np.float32(64)).reshape(n, 1)
+        return p, v
+
+
+def ref_config(sims, k, noise_eps, change_tau_turn, c_puct=5, share=True):
+    cfg = Config()
+    pc = cfg.play
+    pc.simulation_num_per_move = sims
+    pc.parallel_search_num = k
+    pc.noise_eps = noise_eps
+    pc.change_tau_turn = change_tau_turn
+    pc.c_puct = c_puct
+    pc.thinking_loop = 1
+    pc.use_solver_turn = 0
+    pc.use_solver_turn_in_simulation = 0
+    pc.resign_threshold = None
+    pc.share_mtcs_info_in_self_play = share
+    return cfg
+
+
+def ref_selfplay_game(cfg, api):
+    """worker/self_play.py:139-175 loop, driven directly (no process pool / files)."""
+    env = ReversiEnv().reset()
+    info = ReversiPlayer.create_mtcs_info() if cfg.play.share_mtcs_info_in_self_play else None
+    black = ReversiPlayer(cfg, None, enable_resign=False, mtcs_info=info, api=api)
+    white = ReversiPlayer(cfg, None, enable_resign=False, mtcs_info=info, api=api)
+    plies = []
+    from reversi_zero.agent.player import CounterKey
+    while not env.done:
+        if env.next_player == Player.black:
+            pl, own, enemy = black, env.board.black, env.board.white
+        else:
+            pl, own, enemy = white, env.board.white, env.board.black
+        a = pl.action_with_evaluation(own, enemy)
+        key = CounterKey(own, enemy, Player.black.value)
+        plies.append(dict(pid=env.next_player.value, own=int(own), enemy=int(enemy), action=int(a.action),
+                          N=[int(x) for x in pl.var_n[key]], W=[float(x) for x in pl.var_w[key]],
+                          n=float(a.n), q=float(a.q)))
+        env.step(a.action)
+    z = {Winner.black: 1, Winner.white: -1, Winner.draw: 0}[env.winner]
+    black.finish_game(z)
+    white.finish_game(-z)
+    recs = [[[int(m[0][0]), int(m[0][1])], [float(x) for x in m[1]], int(m[2])] for m in black.moves + white.moves]
+    return plies, recs, z
+
+
+def gen_mcts():
+    out = {}
+    for name, sims, share in (("k1_s30_shared", 30, True), ("k1_s12_separate", 12, False)):
+        api = FakeNet()
+        cfg = ref_config(sims=sims, k=1, noise_eps=0, change_tau_turn=0, share=share)
+        plies, recs, z = ref_selfplay_game(cfg, api)
+        import hashlib
+        digest = hashlib.sha256(json.dumps(recs).encode()).hexdigest()
+        out[name] = dict(sims=sims, share=share, c_puct=5, plies=plies, z=z, n_records=len(recs), records_sha256=digest,
+                         records_head=recs[:16], expansions=api.rows)
+    # statistical: K=8 with Dirichlet noise, one mid-game root, many repetitions
+    own, enemy = 0x00000000081d0603, 0x0002043814020100
+    reps, sims = 150, 100
+    acc = np.zeros(64)
+    np.random.seed(12345)
+    for r in range(reps):
+        cfg = ref_config(sims=sims, k=8, noise_eps=0.25, change_tau_turn=0)
+        pl = ReversiPlayer(cfg, None, enable_resign=False, api=FakeNet())
+        pl.action_with_evaluation(own, enemy)
+        from reversi_zero.agent.player import CounterKey
+        n = pl.var_n[CounterKey(own, enemy, 1)]
+        acc += n / n.sum()
+    out["k8_noise_stat"] = dict(own=own, enemy=enemy, sims=sims, reps=reps, c_puct=5, mean_visit_frac=list(acc / reps))
+    return out
+
+
+def main():
+    kats = gen_bitboard()
+    env = gen_env()
+    sym = gen_symmetry()
+    mcts = gen_mcts()
+    with open(os.path.join(HERE, "kats.json"), "w") as f:
+        json.dump(kats, f)
+    with open(os.path.join(HERE, "env.json"), "w") as f:
+        json.dump(env, f)
+    with open(os.path.join(HERE, "symmetry.json"), "w") as f:
+        json.dump(sym, f)
+    with open(os.path.join(HERE, "mcts.json"), "w") as f:
+        json.dump(mcts, f)
+    print("golden vectors written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

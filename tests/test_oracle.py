@@ -1,0 +1,146 @@
+"""Pin the CPU oracle (oracle/) against the golden vectors generated from the unmodified reference
+(tests/golden/make_golden.py) and against the reference's own KATs (test/lib/test_bitboard.py:11-112,
+test/agent/test_player.py:11-75)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+
+from oracle import bitboard as bb
+from oracle import mcts, nn
+
+U64 = np.uint64
+
+
+def _load(golden_dir, name):
+    with open(os.path.join(golden_dir, name)) as f:
+        return json.load(f)
+
+
+def test_reference_kats(golden_dir):
+    # integers quoted in SURVEY §8(c) from the reference's ASCII boards
+    assert bb.find_correct_moves(0x00000000081d0603, 0x0002043814020100) == 0x0000780623000000
+    assert bb.find_correct_moves(0x000700542a202020, 0x0088ffabd5dfdf5f) == 0x0870000000000080
+    assert bb.find_correct_moves(0x008e868ef9fffd7c, 0xfe71797106000203) == 0x0100000000000000
+    assert bb.find_correct_moves(0xfe71797106000203, 0x008e868ef9fffd7c) == 0x0000000000000080
+    for k in _load(golden_dir, "kats.json"):
+        assert bb.find_correct_moves(k["black"], k["white"]) == k["legal_black"]
+        assert bb.find_correct_moves(k["white"], k["black"]) == k["legal_white"]
+
+
+def test_bitboard_vectors(golden_dir):
+    g = np.load(os.path.join(golden_dir, "bitboard.npz"))
+    own, enemy, pos = g["own"], g["enemy"], g["pos"]
+    assert np.array_equal(bb.find_correct_moves_batch(own, enemy), g["legal"])
+    assert np.array_equal(bb.calc_flip_batch(pos, own, enemy), g["flip"])
+    for row, i in zip(g["flip_all"], g["sub"]):
+        got = bb.calc_flip_batch(np.arange(64, dtype=np.uint8), np.full(64, own[i]), np.full(64, enemy[i]))
+        assert np.array_equal(got, row)
+    for name, t in (("flip_vertical", 4), ("rotate90", 1), ("rotate180", 2)):
+        assert np.array_equal(bb.dihedral_batch(own, np.full(own.size, t, np.uint8)), g[name])
+    assert all(bb.flip_diag_a1h8(int(x)) == int(y) for x, y in zip(own[:200], g["flip_diag"][:200]))
+    assert all(bb.bit_count(int(x)) == int(c) for x, c in zip(own[:500], g["bit_count"][:500]))
+
+
+def test_env_playouts(golden_dir):
+    g = _load(golden_dir, "env.json")
+    for game in g["games"] + g["special"]:
+        env = bb.Env().reset()
+        assert list(env.state()) == game["states"][0]
+        for i, a in enumerate(game["actions"]):
+            if "legals" in game:
+                own, enemy = env.own_enemy()
+                assert bb.find_correct_moves(own, enemy) == game["legals"][i]
+            env.step(None if a < 0 else a)
+            assert list(env.state()) == game["states"][i + 1], (game["tag"], i)
+    for u in g["update"]:
+        assert list(bb.Env().update(*u["args"]).state()) == u["state"]
+    low = g["games"][0]
+    assert low["actions"][:6] == [19, 18, 17, 9, 1, 0] and low["states"][-1][5] == 2  # SURVEY §8(c) regression vector
+
+
+def test_symmetry_records(golden_dir):
+    g = _load(golden_dir, "symmetry.json")
+    for case in g["records"]:
+        got = list(mcts.symmetries8(case["own"], case["enemy"], np.array(case["policy"])))
+        assert len(got) == 8
+        for (o, e, p), ((ro, re), rp) in zip(got, case["records"]):
+            assert (o, e) == (ro, re)
+            assert list(p) == rp
+    for inv in g["inverse"]:
+        t = inv["flip"] * 4 + inv["rot"]
+        assert bb.dihedral(inv["board"], t) == inv["transformed"]
+        assert list(mcts.inverse_policy(np.arange(64), t)) == inv["src_index"]
+
+
+def test_reference_test_player_orientation():
+    """test/agent/test_player.py:11-75 restated on the oracle's symmetries8."""
+    idx = lambda x, y: y * 8 + x
+    own = (1 << idx(0, 0)) | (1 << idx(1, 1))
+    enemy = (1 << idx(7, 6)) | (1 << idx(7, 7))
+    policy = np.zeros(64); policy[idx(7, 0)] = 0.8; policy[idx(0, 7)] = 0.2
+    recs = list(mcts.symmetries8(own, enemy, policy))
+    chk = lambda b, x, y: (b >> idx(x, y)) & 1 == 1
+    o, e, p = recs[1]
+    assert chk(o, 7, 0) and chk(o, 6, 1) and chk(e, 0, 7) and chk(e, 1, 7) and p[idx(7, 7)] == 0.8 and p[idx(0, 0)] == 0.2
+    o, e, p = recs[2]
+    assert chk(o, 7, 7) and chk(o, 6, 6) and chk(e, 0, 0) and chk(e, 0, 1) and p[idx(0, 7)] == 0.8 and p[idx(7, 0)] == 0.2
+    o, e, p = recs[5]
+    assert chk(o, 0, 0) and chk(o, 1, 1) and chk(e, 6, 7) and chk(e, 7, 7) and p[idx(0, 7)] == 0.8 and p[idx(7, 0)] == 0.2
+
+
+def _oracle_game(sims, share, k=1, noise=0.0, tau=0, seed=7):
+    pp = mcts.PlayParams(simulation_num_per_move=sims, parallel_search_num=k, noise_eps=noise, change_tau_turn=tau,
+                         c_puct=5, thinking_loop=1, resign_threshold=None, share_mtcs_info_in_self_play=share)
+    return mcts.SelfPlayGame(pp, nn.FakeNetAPI(), seed=seed, game_id=0).play()
+
+
+def test_mcts_exact_vs_reference(golden_dir):
+    """parallel_search_num = 1, deterministic evaluator, tau = 0: the reference is deterministic and the
+    oracle must reproduce its root visit counts, W sums, moves and training records exactly."""
+    g = _load(golden_dir, "mcts.json")
+    for name in ("k1_s30_shared", "k1_s12_separate"):
+        ref = g[name]
+        game = _oracle_game(ref["sims"], ref["share"])
+        assert len(game.plies) == len(ref["plies"])
+        for mine, theirs in zip(game.plies, ref["plies"]):
+            assert (mine["pid"], mine["own"], mine["enemy"]) == (theirs["pid"], theirs["own"], theirs["enemy"])
+            assert list(mine["N"]) == theirs["N"], name
+            assert mine["action"] == theirs["action"]
+            assert abs(mine["q"] - theirs["q"]) < 1e-6
+        assert game.black_z == ref["z"]
+        recs = game.records()
+        assert len(recs) == ref["n_records"]
+        norm = [[[int(o), int(e)], [float(x) for x in p], int(z)] for (o, e), p, z in recs]
+        assert norm[:16] == ref["records_head"]
+        assert hashlib.sha256(json.dumps(norm).encode()).hexdigest() == ref["records_sha256"]
+        assert game.n_expand == ref["expansions"]
+
+
+def test_mcts_statistical_vs_reference(golden_dir):
+    """K = 8 + Dirichlet noise: compare mean root visit fractions (reference: 150 repetitions)."""
+    ref = _load(golden_dir, "mcts.json")["k8_noise_stat"]
+    pp = mcts.PlayParams(simulation_num_per_move=ref["sims"], parallel_search_num=8, noise_eps=0.25, change_tau_turn=0,
+                         c_puct=ref["c_puct"], resign_threshold=None)
+    acc = np.zeros(64)
+    reps = 150
+    for r in range(reps):
+        game = mcts.SelfPlayGame(pp, nn.FakeNetAPI(), seed=99, game_id=r)
+        game.search(ref["own"], ref["enemy"], 1)
+        n = game.table[(ref["own"], ref["enemy"])].N
+        acc += n / n.sum()
+    mine, theirs = acc / reps, np.array(ref["mean_visit_frac"])
+    assert set(np.nonzero(mine)[0]) == set(np.nonzero(theirs)[0])
+    assert np.abs(mine - theirs).max() < 0.04, np.abs(mine - theirs).max()
+
+
+def test_oracle_nn_shapes():
+    from reversi_zero_b200.agent import model as M
+    mc = M.ModelConfig(cnn_filter_num=16, res_layer_num=1, value_fc_size=16)
+    w = M.build_random_weights(mc, 1, perturb_bn=True)
+    assert M.blob_to_weights(mc, M.weights_to_blob(mc, w)).keys() == w.keys()
+    planes = nn.planes_from_bitboards([0x0000000810000000, 3], [0x0000001008000000, 12])
+    p, v = nn.forward(w, planes, 1)
+    assert p.shape == (2, 64) and v.shape == (2,) and np.allclose(p.sum(1), 1, atol=1e-5)
+    assert planes[0, 0, 3, 4] == 1 and planes[0, 1, 3, 3] == 1  # bit 28 = (y=3,x=4)
