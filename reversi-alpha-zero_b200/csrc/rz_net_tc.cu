@@ -1,0 +1,491 @@
+// rz_net_tc.cu -- K4/K5: fused persistent tcgen05 residual tower + heads for the 256-filter network.
+//
+// One CTA per SM, each CTA owns a tile of TWO boards (M = 128 pixel rows) and carries it through the
+// WHOLE network without touching HBM in between:
+//   * activations live in shared memory as fp16 in the UMMA "K-major, no-swizzle" canonical layout,
+//     with a one-pixel zero border, so that each of the nine 3x3 taps is just a different start
+//     address of the same buffer (implicit GEMM, no im2col copy):
+//         chunk(cg, slot, xp) at cg*2896 + slot*144 + xp*16 bytes   (8 channels = 16 B per chunk)
+//         slot = 2*(y+1) + board (the two boards' rows are interleaved so that a dy shift is a
+//         uniform 2-slot offset), xp = x+1; xp = 9 of one slot aliases xp = 0 of the next (shared
+//         zero chunk).  MMA row m = (2y+board)*8 + x  ->  8-row core matrices are board rows.
+//   * weights (fp16, 1.18 MB per conv, L2-resident) are streamed by a producer thread with
+//     cp.async.bulk in pre-packed 32 KB stages (one tap x 64 input channels x 256 output channels)
+//     through a 3-deep mbarrier ring;
+//   * one thread issues tcgen05.mma (M=128, N=256, K=16, fp16 in / fp32 accumulate): 144 MMAs per conv
+//     layer into a 256-column TMEM accumulator;
+//   * eight epilogue warps read the accumulator with tcgen05.ld, apply the folded BatchNorm
+//     (scale, shift), the residual (kept in fp32 in the other 256 TMEM columns) and ReLU, and write the
+//     next layer's fp16 activations straight back into the shared-memory operand buffer;
+//   * the first conv (2 -> 256 channels, K = 18 padded to 32) is a 2-MMA GEMM on an im2col tile built
+//     from the two bitboards; the policy / value heads run on the epilogue warps from the fp32 tower
+//     output.
+// HBM traffic per position: 16 B in, 260 B out.  Algorithmic work: 2 * 755,343,616 flop.
+#include "rz_bitboard.cuh"
+#include "rz_net.cuh"
+
+namespace rz {
+namespace tc {
+
+constexpr int kThreads = 320;  // warp 0 producer, warp 1 MMA issuer + TMEM owner, warps 2..9 epilogue
+constexpr int kEpiThreads = 256;
+constexpr uint32_t kActCg = 2896, kActSlot = 144;
+constexpr uint32_t kActBytes = 32 * kActCg;  // 92,672
+constexpr uint32_t kStageBytes = 32768, kStages = 3;
+constexpr uint32_t kA0Bytes = 8192, kW0Bytes = 16384;
+constexpr uint32_t kOffAct = 0;
+constexpr uint32_t kOffW = kOffAct + kActBytes;
+constexpr uint32_t kOffA0 = kOffW + kStages * kStageBytes;
+constexpr uint32_t kOffW0 = kOffA0 + kA0Bytes;
+constexpr uint32_t kOffSS = kOffW0 + kW0Bytes;           // 2 x [scale 256][shift 256] fp32
+constexpr uint32_t kOffPart = kOffSS + 2 * 2048;         // [2 halves][128 rows][4] fp32 head partial sums
+constexpr uint32_t kOffHp = kOffPart + 2 * 128 * 4 * 4;  // [2 boards][128]
+constexpr uint32_t kOffHv = kOffHp + 2 * 128 * 4;        // [2][64]
+constexpr uint32_t kOffLogit = kOffHv + 2 * 64 * 4;      // [2][64]
+constexpr uint32_t kMaxV = 512;
+constexpr uint32_t kOffFc1 = kOffLogit + 2 * 64 * 4;     // [2][kMaxV]
+constexpr uint32_t kOffBar = kOffFc1 + 2 * kMaxV * 4;    // mbarriers
+constexpr uint32_t kNumBars = 2 * kStages + 3;
+constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
+constexpr uint32_t kSmemBytes = kOffTmemPtr + 16;
+constexpr uint32_t kSmemAlloc = kSmemBytes + 128;  // slack for manual 128 B alignment
+static_assert(kSmemAlloc <= 232448, "shared memory budget exceeded");
+
+// instruction descriptor, kind::f16: D = f32 (bits 4-5 = 1), A = B = f16 (0), K-major both,
+// N >> 3 at bits 17-22, M >> 4 at bits 24-28
+constexpr uint32_t kIdesc = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait (~4 s of SM clocks): a protocol bug traps and is reported to the host instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    long long t0 = 0;
+    for (uint32_t spin = 0; !ok; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!ok && (spin & 1023) == 1023) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000LL) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_NONE; core matrix = 8 rows x 16 B (rows 16 B apart);
+// LBO = byte distance between the two K-halves of one MMA, SBO = byte distance between 8-row groups.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+           (1ULL << 46);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+        "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+        "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(fminf(a, 65504.f), fminf(b, 65504.f));  // inputs are >= 0 (post-ReLU)
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+struct Params {
+    const __half* w0;   // layer-0 weight image (16 KB)
+    const __half* w;    // tower weight stages
+    const float* ss;    // folded BN [L][2][256], then heads
+    const float* blob;  // fp32 blob for the head weights
+    size_t off_policy_conv, off_policy_fc_k, off_policy_fc_b, off_value_conv, off_value_fc1_k, off_value_fc1_b, off_value_fc2_k,
+        off_value_fc2_b;
+    const u64* own;
+    const u64* enemy;
+    float* policy;
+    float* value;
+    float* dbg_tower;  // nullable
+    uint32_t n;
+    int n_layers;  // 1 + 2R
+    int V;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) net_tower_kernel(const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+    uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = base + kOffBar;
+    auto bar_full = [&](uint32_t s) { return bar0 + s * 8; };
+    auto bar_empty = [&](uint32_t s) { return bar0 + (kStages + s) * 8; };
+    const uint32_t bar_w0 = bar0 + 2 * kStages * 8, bar_a = bar_w0 + 8, bar_acc = bar_w0 + 16;
+    const uint32_t ntiles = (p.n + 1) >> 1;
+    const int L = p.n_layers;
+
+    // ---- one-time setup -----------------------------------------------------------------------------
+    for (uint32_t i = threadIdx.x * 16; i < kActBytes; i += kThreads * 16) *reinterpret_cast<uint4*>(sm + kOffAct + i) = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < kStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+        mbar_init(bar_w0, 1);
+        mbar_init(bar_a, kEpiThreads);
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: all 512 columns (this kernel is the only resident CTA on its SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(base + kOffTmemPtr) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + kOffTmemPtr);
+    const uint32_t tm_acc = tmem, tm_res = tmem + 256;
+
+    if (warp == 0) {
+        // ===== weight producer =====================================================================
+        if (lane == 0) {
+            mbar_expect_tx(bar_w0, kW0Bytes);
+            bulk_g2s(base + kOffW0, p.w0, kW0Bytes, bar_w0);
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int l = 1; l < L; ++l) {
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w) + (size_t)(l - 1) * 36 * kStageBytes;
+                    for (int s = 0; s < 36; ++s) {
+                        mbar_wait(bar_empty(stage), phase ^ 1);
+                        mbar_expect_tx(bar_full(stage), kStageBytes);
+                        bulk_g2s(base + kOffW + stage * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes, bar_full(stage));
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer ==========================================================================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, a_par = 0;
+            bool first = true;
+            for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int l = 0; l < L; ++l) {
+                    mbar_wait(bar_a, a_par);
+                    a_par ^= 1;
+                    tc_fence_after();
+                    if (l == 0) {
+                        if (first) { mbar_wait(bar_w0, 0); first = false; }
+#pragma unroll
+                        for (uint32_t j = 0; j < 2; ++j)
+                            umma_f16(tm_acc, smem_desc(base + kOffA0 + j * 2 * 2048, 2048, 128),
+                                     smem_desc(base + kOffW0 + j * 2 * 4096, 4096, 128), kIdesc, j);
+                    } else {
+                        for (uint32_t tap = 0; tap < 9; ++tap) {
+                            // tap (kh, kw) reads input pixel (y + kh - 1, x + kw - 1): slot offset 2*kh, chunk offset kw
+                            const uint32_t a_tap = base + kOffAct + (2 * (tap / 3)) * kActSlot + (tap % 3) * 16;
+                            for (uint32_t kb = 0; kb < 4; ++kb) {
+                                mbar_wait(bar_full(stage), phase);
+                                tc_fence_after();
+                                const uint32_t b_st = base + kOffW + stage * kStageBytes;
+#pragma unroll
+                                for (uint32_t j = 0; j < 4; ++j)
+                                    umma_f16(tm_acc, smem_desc(a_tap + (kb * 8 + 2 * j) * kActCg, kActCg, kActSlot),
+                                             smem_desc(b_st + 2 * j * 4096, 4096, 128), kIdesc, (tap | kb | j) != 0);
+                                umma_commit(bar_empty(stage));
+                                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                            }
+                        }
+                    }
+                    umma_commit(bar_acc);
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps (8) ==================================================================
+        const int et = threadIdx.x - 64;        // 0..255
+        const int q = warp & 3;                 // TMEM sub-partition this warp may access
+        const int h = (warp - 2) >> 2;          // column half handled by this warp
+        const int m = q * 32 + lane;            // accumulator row == TMEM lane
+        const int g = m >> 3, x = m & 7, brd = g & 1, y = g >> 1;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        float* ss_s = reinterpret_cast<float*>(sm + kOffSS);
+        float* part = reinterpret_cast<float*>(sm + kOffPart);
+        float* hp = reinterpret_cast<float*>(sm + kOffHp);
+        float* hv = reinterpret_cast<float*>(sm + kOffHv);
+        float* logit = reinterpret_cast<float*>(sm + kOffLogit);
+        float* fc1 = reinterpret_cast<float*>(sm + kOffFc1);
+        const uint32_t act_row = base + kOffAct + (g + 2) * kActSlot + (x + 1) * 16;  // + cg * kActCg
+        const float* ssh = p.ss + (size_t)L * 512;
+        uint32_t acc_par = 0;
+        uint32_t ss_buf = 0;
+
+        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const uint32_t pos0 = tile * 2;
+            const bool valid = pos0 + brd < p.n;
+            // ---- layer-0 operand: im2col of the two bit planes, K index = tap*2 + plane, padded to 32 ----
+            {
+                const u64 o = valid ? p.own[pos0 + brd] : 0, e = valid ? p.enemy[pos0 + brd] : 0;
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    const int kc = 2 * h + kk;
+                    uint32_t w[4];
+#pragma unroll
+                    for (int jp = 0; jp < 4; ++jp) {
+                        uint32_t packed = 0;
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            const int k = kc * 8 + jp * 2 + half;
+                            uint32_t bit = 0;
+                            if (k < 18) {
+                                const int tap = k >> 1, yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+                                if (yy >= 0 && yy < 8 && xx >= 0 && xx < 8) bit = (uint32_t)((((k & 1) ? e : o) >> (yy * 8 + xx)) & 1ULL);
+                            }
+                            packed |= (bit ? 0x3C00u : 0u) << (16 * half);  // fp16 1.0
+                        }
+                        w[jp] = packed;
+                    }
+                    *reinterpret_cast<uint4*>(sm + kOffA0 + kc * 2048 + g * 128 + x * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(bar_a);
+
+            float hp0 = 0.f, hp1 = 0.f, hvv = 0.f;
+            for (int l = 0; l < L; ++l) {
+                // stage this layer's folded BN parameters (double-buffered across layers)
+                float* sc = ss_s + ss_buf * 512;
+                sc[et] = __ldg(p.ss + (size_t)l * 512 + et);
+                sc[256 + et] = __ldg(p.ss + (size_t)l * 512 + 256 + et);
+                ss_buf ^= 1;
+                epi_bar();
+                mbar_wait(bar_acc, acc_par);
+                acc_par ^= 1;
+                tc_fence_after();
+                const bool is_conv2 = l > 0 && (l & 1) == 0;   // second conv of a block: add the skip connection
+                const bool keep_res = l == 0 || is_conv2;      // block output: keep fp32 copy in TMEM
+                const bool last = l == L - 1;
+#pragma unroll 1
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const int c0 = h * 128 + c4 * 32;
+                    uint32_t v[32];
+                    tmem_ld32(tm_acc + lane_sel + c0, v);
+                    if (is_conv2) {
+                        uint32_t r[32];
+                        tmem_ld32(tm_res + lane_sel + c0, r);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            v[j] = __float_as_uint(fmaxf(fmaf(__uint_as_float(v[j]), sc[c0 + j], sc[256 + c0 + j]) + __uint_as_float(r[j]), 0.f));
+                    } else {
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            v[j] = __float_as_uint(fmaxf(fmaf(__uint_as_float(v[j]), sc[c0 + j], sc[256 + c0 + j]), 0.f));
+                    }
+                    if (keep_res && !last) tmem_st32(tm_res + lane_sel + c0, v);
+                    if (!last) {
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            uint4 pk;
+                            pk.x = pack_h2(__uint_as_float(v[jj * 8 + 0]), __uint_as_float(v[jj * 8 + 1]));
+                            pk.y = pack_h2(__uint_as_float(v[jj * 8 + 2]), __uint_as_float(v[jj * 8 + 3]));
+                            pk.z = pack_h2(__uint_as_float(v[jj * 8 + 4]), __uint_as_float(v[jj * 8 + 5]));
+                            pk.w = pack_h2(__uint_as_float(v[jj * 8 + 6]), __uint_as_float(v[jj * 8 + 7]));
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(act_row + ((c0 >> 3) + jj) * kActCg), "r"(pk.x),
+                                         "r"(pk.y), "r"(pk.z), "r"(pk.w)
+                                         : "memory");
+                        }
+                    } else {
+                        // tower output: feed the 1x1 head convolutions directly from registers (fp32)
+                        const float* wp = p.blob + p.off_policy_conv;
+                        const float* wv = p.blob + p.off_value_conv;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float a = __uint_as_float(v[j]);
+                            const float2 w2 = __ldg(reinterpret_cast<const float2*>(wp) + c0 + j);
+                            hp0 = fmaf(a, w2.x, hp0);
+                            hp1 = fmaf(a, w2.y, hp1);
+                            hvv = fmaf(a, __ldg(wv + c0 + j), hvv);
+                        }
+                        if (p.dbg_tower && valid) {
+                            float* d = p.dbg_tower + ((size_t)(pos0 + brd) * 64 + y * 8 + x) * 256 + c0;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]);
+                        }
+                    }
+                }
+                if (!last) {
+                    if (keep_res) tmem_wait_st();
+                    fence_proxy_async();
+                    tc_fence_before();
+                    mbar_arrive(bar_a);
+                }
+            }
+            // ---- heads (agent/model.py:43-56) on the 256 epilogue threads --------------------------------
+            part[(h * 128 + m) * 4 + 0] = hp0;
+            part[(h * 128 + m) * 4 + 1] = hp1;
+            part[(h * 128 + m) * 4 + 2] = hvv;
+            epi_bar();
+            if (h == 0) {
+                const float a0 = part[m * 4 + 0] + part[(128 + m) * 4 + 0];
+                const float a1 = part[m * 4 + 1] + part[(128 + m) * 4 + 1];
+                const float av = part[m * 4 + 2] + part[(128 + m) * 4 + 2];
+                const int pix = y * 8 + x;
+                hp[brd * 128 + pix] = fmaxf(fmaf(a0, ssh[0], ssh[2]), 0.f);        // Flatten is (C,H,W): index c*64 + pix
+                hp[brd * 128 + 64 + pix] = fmaxf(fmaf(a1, ssh[1], ssh[3]), 0.f);
+                hv[brd * 64 + pix] = fmaxf(fmaf(av, ssh[4], ssh[5]), 0.f);
+            }
+            epi_bar();
+            if (et < 128) {  // policy logits: Dense(128 -> 64)
+                const int b = et >> 6, j = et & 63;
+                const float* k = p.blob + p.off_policy_fc_k;
+                float acc = __ldg(p.blob + p.off_policy_fc_b + j);
+#pragma unroll 8
+                for (int i = 0; i < 128; ++i) acc = fmaf(hp[b * 128 + i], __ldg(k + i * 64 + j), acc);
+                logit[b * 64 + j] = acc;
+            }
+            for (int idx = et; idx < 2 * p.V; idx += kEpiThreads) {  // value Dense(64 -> V) + ReLU
+                const int b = idx / p.V, j = idx - b * p.V;
+                const float* k = p.blob + p.off_value_fc1_k;
+                float acc = __ldg(p.blob + p.off_value_fc1_b + j);
+#pragma unroll 8
+                for (int i = 0; i < 64; ++i) acc = fmaf(hv[b * 64 + i], __ldg(k + (size_t)i * p.V + j), acc);
+                fc1[b * kMaxV + j] = fmaxf(acc, 0.f);
+            }
+            epi_bar();
+            const int ew = warp - 2;
+            if (ew < 2) {  // softmax over 64 logits, one warp per board
+                const int b = ew;
+                const float l0 = logit[b * 64 + lane], l1 = logit[b * 64 + 32 + lane];
+                float mx = fmaxf(l0, l1);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
+                float s = e0 + e1;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (pos0 + b < p.n) {
+                    p.policy[(size_t)(pos0 + b) * 64 + lane] = e0 / s;
+                    p.policy[(size_t)(pos0 + b) * 64 + 32 + lane] = e1 / s;
+                }
+            } else if (ew < 4) {  // value Dense(V -> 1) + tanh, one warp per board
+                const int b = ew - 2;
+                float acc = 0.f;
+                for (int j = lane; j < p.V; j += 32) acc = fmaf(fc1[b * kMaxV + j], __ldg(p.blob + p.off_value_fc2_k + j), acc);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0 && pos0 + b < p.n) p.value[pos0 + b] = tanhf(acc + __ldg(p.blob + p.off_value_fc2_b));
+            }
+            // the next tile's layer-0 operand build only touches the A0 region, whose last reader (this tile's
+            // layer-0 MMAs) completed before the first bar_acc of this tile
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// ---- weight packing -----------------------------------------------------------------------------------
+__global__ void pack_w0_kernel(const float* __restrict__ k0, __half* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over [4 kc][256 n][8 j]
+    if (i >= 4 * 256 * 8) return;
+    const int j = i & 7, n = (i >> 3) & 255, kc = i >> 11, k = kc * 8 + j;
+    // conv0.kernel[kh][kw][c][n], K index = (kh*3+kw)*2 + c
+    out[i] = __float2half_rn(k < 18 ? k0[(size_t)k * 256 + n] : 0.f);
+}
+__global__ void pack_w_kernel(const float* __restrict__ blob, size_t off_res0, size_t stride, int n_layers, __half* __restrict__ out) {
+    const size_t total = (size_t)n_layers * 36 * 8 * 256 * 8;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int j = i & 7, n = (i >> 3) & 255, kc = (i >> 11) & 7;
+        const size_t ls = i >> 14;
+        const int s = (int)(ls % 36), l = (int)(ls / 36);
+        const int tap = s >> 2, kb = s & 3, ci = kb * 64 + kc * 8 + j;
+        out[i] = __float2half_rn(blob[off_res0 + (size_t)l * stride + ((size_t)tap * 256 + ci) * 256 + n]);
+    }
+}
+
+}  // namespace tc
+
+int net_pack_tc(rz_net* net, cudaStream_t stream) {
+    tc::pack_w0_kernel<<<(4 * 256 * 8 + 255) / 256, 256, 0, stream>>>(net->blob + net->off_conv0, net->tc_w0);
+    if (net->cfg.res_blocks > 0)
+        tc::pack_w_kernel<<<num_sms() * 8, 256, 0, stream>>>(net->blob, net->off_res0, net->res_stride_conv, 2 * net->cfg.res_blocks, net->tc_w);
+    RZ_LAUNCH_CHECK();
+    return RZ_OK;
+}
+
+int net_forward_tc(rz_net* net, const uint64_t* own, const uint64_t* enemy, float* policy, float* value, size_t n, cudaStream_t stream,
+                   float* dbg_tower) {
+    RZ_REQUIRE(net->cfg.filters == 256, "tcgen05 tower requires 256 filters");
+    RZ_REQUIRE(net->cfg.value_fc <= (int)tc::kMaxV, "tcgen05 tower supports value_fc_size <= %u", tc::kMaxV);
+    RZ_REQUIRE(n < (1ull << 31), "batch too large");
+    static bool attr_set = false;
+    if (!attr_set) {
+        RZ_CUDA_TRY(cudaFuncSetAttribute(tc::net_tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemAlloc));
+        attr_set = true;
+    }
+    tc::Params p;
+    p.w0 = net->tc_w0; p.w = net->tc_w; p.ss = net->scale_shift; p.blob = net->blob;
+    p.off_policy_conv = net->off_policy_conv; p.off_policy_fc_k = net->off_policy_fc_k; p.off_policy_fc_b = net->off_policy_fc_b;
+    p.off_value_conv = net->off_value_conv; p.off_value_fc1_k = net->off_value_fc1_k; p.off_value_fc1_b = net->off_value_fc1_b;
+    p.off_value_fc2_k = net->off_value_fc2_k; p.off_value_fc2_b = net->off_value_fc2_b;
+    p.own = own; p.enemy = enemy; p.policy = policy; p.value = value; p.dbg_tower = dbg_tower;
+    p.n = (uint32_t)n; p.n_layers = 1 + 2 * net->cfg.res_blocks; p.V = net->cfg.value_fc;
+    const uint32_t ntiles = (uint32_t)((n + 1) / 2);
+    const uint32_t grid = ntiles < (uint32_t)num_sms() ? ntiles : (uint32_t)num_sms();
+    tc::net_tower_kernel<<<grid, tc::kThreads, tc::kSmemAlloc, stream>>>(p);
+    RZ_LAUNCH_CHECK();
+    return RZ_OK;
+}
+
+}  // namespace rz

@@ -1,0 +1,61 @@
+"""K1 microbenchmark (BASELINE.json config 5): 10M positions resident in HBM, CUDA-event timing over
+back-to-back launches; inputs (160 MB + outputs) exceed the 126 MB L2.  Prints one JSON object."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "reversi-alpha-zero_b200"))
+
+
+def run(n=10_000_000, iters=100, warmup=5):
+    import torch
+    from reversi_zero_b200 import _cabi, device as D
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    rng = np.random.default_rng(20260922)
+    a = rng.integers(0, 2 ** 64, size=n, dtype=np.uint64)
+    b = rng.integers(0, 2 ** 64, size=n, dtype=np.uint64)
+    r = rng.integers(0, 2 ** 64, size=n, dtype=np.uint64)
+    own, enemy = a & r, a & ~r
+    pos = rng.integers(0, 64, size=n, dtype=np.uint8)
+    d_own, d_enemy, d_pos = D.to_device(own), D.to_device(enemy), D.to_device(pos)
+    d_out = D.empty(n, np.uint64)
+    lib = _cabi.lib()
+    s = torch.cuda.current_stream()
+    res = {}
+    for name, bytes_per, call in (
+        ("find_correct_moves", 24, lambda: lib.rz_find_correct_moves_dev(D.ptr(d_own), D.ptr(d_enemy), D.ptr(d_out), n, D.stream_ptr(s))),
+        ("calc_flip", 25, lambda: lib.rz_calc_flip_dev(D.ptr(d_pos), D.ptr(d_own), D.ptr(d_enemy), D.ptr(d_out), n, D.stream_ptr(s))),
+    ):
+        for _ in range(warmup):
+            _cabi.check(call(), name)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        for _ in range(iters):
+            call()
+        e1.record(s)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        gbs = n * bytes_per / ms / 1e6
+        res[name] = dict(ms=ms, gpos_per_s=n / ms / 1e6, gbs=gbs, frac_of_measured_hbm=gbs / hbm, bytes_per_position=bytes_per)
+    # CPU oracle on one core for scale
+    from oracle import bitboard as ob
+    t = time.time(); ob.find_correct_moves_batch(own[:2_000_000], enemy[:2_000_000]); dt = time.time() - t
+    res["cpu_oracle_find_correct_moves_mpos_per_s_1core"] = 2.0 / dt
+    res["n"] = n
+    res["hbm_peak_gbs"] = hbm
+    return res
+
+
+if __name__ == "__main__":
+    print(json.dumps(run()))
