@@ -68,8 +68,10 @@ __device__ __forceinline__ void conv3x3_layer(const float* __restrict__ in, floa
 template <int PIX>
 __global__ void __launch_bounds__(kGThreads) net_generic_kernel(const float* __restrict__ blob, const float* __restrict__ ss,
                                                                 rz_net net, const u64* __restrict__ own, const u64* __restrict__ enemy,
-                                                                float* __restrict__ policy, float* __restrict__ value, size_t n) {
+                                                                float* __restrict__ policy, float* __restrict__ value, size_t n,
+                                                                const uint32_t* __restrict__ n_dev) {
     extern __shared__ float smem[];
+    if (n_dev) n = *n_dev;
     const int F = net.cfg.filters, R = net.cfg.res_blocks, V = net.cfg.value_fc;
     float* bufA = smem;               // [F][100]
     float* bufB = smem + F * 100;     // [F][100]
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(kGThreads) net_generic_kernel(const float* __r
 }
 
 int net_forward_generic(rz_net* net, const uint64_t* own, const uint64_t* enemy, float* policy, float* value, size_t n,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, const uint32_t* n_dev) {
     const int F = net->cfg.filters, V = net->cfg.value_fc;
     RZ_REQUIRE(F >= 2 && F <= 256, "generic kernel supports 2 <= filters <= 256 (got %d)", F);
     const size_t smem = ((size_t)2 * F * 100 + 128 + 64 + (V > 64 ? V : 64)) * sizeof(float);
@@ -160,7 +162,7 @@ int net_forward_generic(rz_net* net, const uint64_t* own, const uint64_t* enemy,
 #define RZ_LAUNCH_G(P)                                                                                             \
     do {                                                                                                           \
         RZ_CUDA_TRY(cudaFuncSetAttribute(net_generic_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        net_generic_kernel<P><<<(unsigned)blocks, kGThreads, smem, stream>>>(net->blob, net->scale_shift, *net, own, enemy, policy, value, n); \
+        net_generic_kernel<P><<<(unsigned)blocks, kGThreads, smem, stream>>>(net->blob, net->scale_shift, *net, own, enemy, policy, value, n, n_dev); \
     } while (0)
     switch (pix) {
         case 64: RZ_LAUNCH_G(64); break;
@@ -185,6 +187,14 @@ int net_forward(rz_net* net, const uint64_t* own, const uint64_t* enemy, float* 
     }
     RZ_REQUIRE(impl == RZ_NET_IMPL_GENERIC, "unknown net impl %d", impl);
     return net_forward_generic(net, own, enemy, policy, value, n, stream);
+}
+
+int net_forward_counted(rz_net* net, const uint64_t* own, const uint64_t* enemy, float* policy, float* value,
+                        const uint32_t* count_dev, size_t max_n, int impl, cudaStream_t stream) {
+    if (!net->loaded) { set_error("rz_net: weights not loaded"); return RZ_ESTATE; }
+    if (impl == RZ_NET_IMPL_AUTO) impl = net->cfg.filters == 256 ? RZ_NET_IMPL_TCGEN05 : RZ_NET_IMPL_GENERIC;
+    if (impl == RZ_NET_IMPL_TCGEN05) return net_forward_tc(net, own, enemy, policy, value, max_n, stream, nullptr, count_dev);
+    return net_forward_generic(net, own, enemy, policy, value, max_n, stream, count_dev);
 }
 
 static int finish_load(rz_net* net, cudaStream_t stream) {

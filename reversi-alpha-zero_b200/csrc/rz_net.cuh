@@ -36,9 +36,13 @@ inline int n_conv_layers(const rz_net_cfg& c) { return 1 + 2 * c.res_blocks; }
 inline size_t ss_floats(const rz_net_cfg& c) { return (size_t)n_conv_layers(c) * 2 * c.filters + 4 + 2; }
 
 int net_forward_generic(rz_net* net, const uint64_t* own, const uint64_t* enemy, float* policy, float* value, size_t n,
-                        cudaStream_t stream);
+                        cudaStream_t stream, const uint32_t* n_dev = nullptr);
+// batch size known only on the device (count_dev), at most max_n
+int net_forward_counted(rz_net* net, const uint64_t* own, const uint64_t* enemy, float* policy, float* value,
+                        const uint32_t* count_dev, size_t max_n, int impl, cudaStream_t stream);
 int net_forward_tc(rz_net* net, const uint64_t* own, const uint64_t* enemy, float* policy, float* value, size_t n,
-                   cudaStream_t stream, float* dbg_tower /* nullable: [n][64][256] fp32 tower output */);
+                   cudaStream_t stream, float* dbg_tower /* nullable: [n][64][256] fp32 tower output */,
+                   const uint32_t* n_dev = nullptr /* nullable: actual batch size in device memory (<= n) */);
 int net_pack_tc(rz_net* net, cudaStream_t stream);
 int net_forward(rz_net* net, const uint64_t* own, const uint64_t* enemy, float* policy, float* value, size_t n, int impl,
                 cudaStream_t stream);

@@ -158,11 +158,14 @@ struct Params {
     float* value;
     float* dbg_tower;  // nullable
     uint32_t n;
+    const uint32_t* n_dev;  // nullable: batch size produced on the device (engine waves)
     int n_layers;  // 1 + 2R
     int V;
 };
 
-__global__ void __launch_bounds__(kThreads, 1) net_tower_kernel(const Params p) {
+__global__ void __launch_bounds__(kThreads, 1) net_tower_kernel(const Params pp) {
+    Params p = pp;
+    if (p.n_dev) p.n = *p.n_dev;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -465,7 +468,7 @@ int net_pack_tc(rz_net* net, cudaStream_t stream) {
 }
 
 int net_forward_tc(rz_net* net, const uint64_t* own, const uint64_t* enemy, float* policy, float* value, size_t n, cudaStream_t stream,
-                   float* dbg_tower) {
+                   float* dbg_tower, const uint32_t* n_dev) {
     RZ_REQUIRE(net->cfg.filters == 256, "tcgen05 tower requires 256 filters");
     RZ_REQUIRE(net->cfg.value_fc <= (int)tc::kMaxV, "tcgen05 tower supports value_fc_size <= %u", tc::kMaxV);
     RZ_REQUIRE(n < (1ull << 31), "batch too large");
@@ -480,7 +483,7 @@ int net_forward_tc(rz_net* net, const uint64_t* own, const uint64_t* enemy, floa
     p.off_value_conv = net->off_value_conv; p.off_value_fc1_k = net->off_value_fc1_k; p.off_value_fc1_b = net->off_value_fc1_b;
     p.off_value_fc2_k = net->off_value_fc2_k; p.off_value_fc2_b = net->off_value_fc2_b;
     p.own = own; p.enemy = enemy; p.policy = policy; p.value = value; p.dbg_tower = dbg_tower;
-    p.n = (uint32_t)n; p.n_layers = 1 + 2 * net->cfg.res_blocks; p.V = net->cfg.value_fc;
+    p.n = (uint32_t)n; p.n_dev = n_dev; p.n_layers = 1 + 2 * net->cfg.res_blocks; p.V = net->cfg.value_fc;
     const uint32_t ntiles = (uint32_t)((n + 1) / 2);
     const uint32_t grid = ntiles < (uint32_t)num_sms() ? ntiles : (uint32_t)num_sms();
     tc::net_tower_kernel<<<grid, tc::kThreads, tc::kSmemAlloc, stream>>>(p);

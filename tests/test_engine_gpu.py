@@ -1,0 +1,121 @@
+"""GPU parity tests of the on-device MCTS engine against the CPU oracle (oracle/mcts.py, itself pinned
+to the unmodified reference) with the deterministic evaluator: root statistics, whole games (moves,
+visit counts, results) and the play_data file must be IDENTICAL; every engine game is additionally
+replayed through the oracle's ReversiEnv restatement (replay parity)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bitboard as ob
+from oracle import mcts, nn as onn
+from reversi_zero_b200 import engine as E
+
+pytestmark = pytest.mark.gpu
+
+
+def params(**kw):
+    base = dict(simulation_num_per_move=40, parallel_search_num=8, noise_eps=0.0, change_tau_turn=4, c_puct=5,
+                thinking_loop=1, resign_threshold=None, share_mtcs_info_in_self_play=True)
+    base.update(kw)
+    return mcts.PlayParams(**base)
+
+
+def make_engine(pp, games, seed, **kw):
+    cfg = E.engine_cfg_from_play_config(pp, games=games, seed=seed, eval_mode=E.EVAL_FAKE, **kw)
+    return E.Engine(cfg)
+
+
+@pytest.mark.parametrize("k,sims", [(1, 30), (8, 100), (4, 57)])
+def test_search_root_exact(k, sims):
+    own, enemy = 0x00000000081d0603, 0x0002043814020100
+    pp = params(parallel_search_num=k, simulation_num_per_move=sims)
+    eng = make_engine(pp, games=3, seed=11)
+    for slot in range(3):
+        n, w = eng.search_root(own, enemy, 1, slot)
+        game = mcts.SelfPlayGame(pp, onn.FakeNetAPI(), seed=11, game_id=slot)
+        game.search(own, enemy, 1)
+        node = game.table[(own, enemy)]
+        assert list(n) == list(node.N), (k, sims, slot)
+        assert np.array_equal(w, node.W)
+    eng.close()
+
+
+def replay_check(g):
+    """replay the engine's move list through the oracle env: every intermediate state must agree."""
+    env = ob.Env().reset()
+    for ply in g["plies"]:
+        own, enemy = env.own_enemy()
+        assert (ply["own"], ply["enemy"], ply["pid"]) == (own, enemy, env.next_player)
+        legal = ob.find_correct_moves(own, enemy)
+        assert all((legal >> a) & 1 for a in np.nonzero(ply["N"])[0])
+        assert ply["action"] == -1 or (legal >> ply["action"]) & 1
+        env.step(None if ply["action"] < 0 else ply["action"])
+    assert env.done and env.winner == g["winner"] and (env.black, env.white) == (g["black"], g["white"])
+    assert env.turn == g["turn"]
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(share_mtcs_info_in_self_play=False, simulation_num_per_move=24),
+                                dict(thinking_loop=3, required_visit_to_decide_action=30, start_rethinking_turn=2,
+                                     simulation_num_per_move=20),
+                                dict(resign_threshold=-0.3, allowed_resign_turn=10, disable_resignation_rate=0.5,
+                                     simulation_num_per_move=20, change_tau_turn=60)])
+def test_full_games_exact(kw, tmp_path):
+    pp = params(**kw)
+    n_games = 6
+    eng = make_engine(pp, games=4, seed=21, max_games=n_games)  # 4 slots, 6 games: slots 0,1 play two games each
+    eng.run(finished_target=n_games)
+    raw_games, ng, raw_plies, _ = eng.poll_raw()
+    assert ng == n_games
+    path = str(tmp_path / "play_test.json")
+    nrec = E.write_play_data(path, raw_games, ng, raw_plies, pp.save_policy_of_tau_1, pp.change_tau_turn)
+    # re-read through poll()'s python view
+    games = []
+    for i in range(ng):
+        g = raw_games[i]
+        games.append(dict(game_id=int(g.game_id), winner=int(g.winner), black=int(g.black), white=int(g.white), turn=int(g.turn),
+                          black_z=int(g.black_z), expansions=int(g.expansions), resigned_mask=int(g.resigned_mask),
+                          plies=[dict(own=int(raw_plies[j].own), enemy=int(raw_plies[j].enemy), pid=int(raw_plies[j].player),
+                                      action=int(raw_plies[j].action), N=np.array(raw_plies[j].n_visit[:]), loops=int(raw_plies[j].loops),
+                                      recorded=int(raw_plies[j].recorded), q=float(raw_plies[j].q), n=float(raw_plies[j].n))
+                                 for j in range(g.first_ply, g.first_ply + g.n_plies)]))
+    expected_records = []
+    for g in sorted(games, key=lambda x: x["game_id"]):
+        replay_check(g)
+        o = mcts.SelfPlayGame(pp, onn.FakeNetAPI(), seed=21, game_id=g["game_id"]).play()
+        rec_plies = [p for p in g["plies"] if p["recorded"]]
+        assert len(rec_plies) == len(o.plies)
+        for mine, theirs in zip(rec_plies, o.plies):
+            assert (mine["own"], mine["enemy"], mine["pid"]) == (theirs["own"], theirs["enemy"], theirs["pid"])
+            assert list(mine["N"]) == list(theirs["N"])
+            assert mine["action"] == theirs["action"] and mine["loops"] == theirs["loops"]
+            assert abs(mine["q"] - theirs["q"]) < 1e-6 and mine["n"] == theirs["n"]
+        assert g["black_z"] == o.black_z and g["winner"] == o.env.winner and g["expansions"] == o.n_expand
+        assert g["resigned_mask"] == (1 if o.resigned[1] else 0) | (2 if o.resigned[2] else 0)
+    # file content: same records, same text as json.dumps of the oracle's reference-format records
+    for i in range(ng):  # file order = poll order
+        g = games[i]
+        o = mcts.SelfPlayGame(pp, onn.FakeNetAPI(), seed=21, game_id=g["game_id"]).play()
+        expected_records += [[[int(a), int(b)], [float(x) for x in p], int(z)] for (a, b), p, z in o.records()]
+    assert nrec == len(expected_records)
+    text = open(path).read()
+    assert text == json.dumps(expected_records)
+    st = eng.stats()
+    assert st["games_finished"] == n_games and st["expansions"] == sum(g["expansions"] for g in games)
+    eng.close()
+
+
+def test_noise_statistics(golden_dir):
+    """Dirichlet root noise + K = 8: mean root visit fractions vs the reference (golden, 150 repetitions)."""
+    ref = json.load(open(os.path.join(golden_dir, "mcts.json")))["k8_noise_stat"]
+    pp = params(simulation_num_per_move=ref["sims"], noise_eps=0.25, c_puct=ref["c_puct"])
+    eng = make_engine(pp, games=256, seed=5)
+    acc = np.zeros(64)
+    for slot in range(0, 256, 2):  # every call searches all slots; read a different one each time
+        n, _ = eng.search_root(ref["own"], ref["enemy"], 1, slot)
+        acc += n / n.sum()
+    mine, theirs = acc / 128, np.array(ref["mean_visit_frac"])
+    assert set(np.nonzero(mine)[0]) == set(np.nonzero(theirs)[0])
+    assert np.abs(mine - theirs).max() < 0.04, np.abs(mine - theirs).max()
+    eng.close()

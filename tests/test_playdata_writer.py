@@ -1,0 +1,70 @@
+"""CPU test of the play_data writer (host code of the C-ABI library): feed it the oracle's game log and
+require the file to be byte-identical to json.dumps of the reference-format records, and loadable by
+the reference's own convert_to_training_data logic (worker/optimize.py:215-231, restated)."""
+import json
+
+import numpy as np
+import pytest
+
+from oracle import mcts, nn as onn, bitboard as ob
+from reversi_zero_b200 import _cabi, engine as E
+
+
+def to_ctypes(games):
+    n_plies = sum(len(g.plies) for g in games)
+    G = (_cabi.Game * len(games))()
+    P = (_cabi.Ply * max(n_plies, 1))()
+    at = 0
+    for i, g in enumerate(games):
+        G[i].game_id = g.game_id; G[i].first_ply = at; G[i].n_plies = len(g.plies); G[i].black_z = g.black_z
+        G[i].winner = g.env.winner
+        for rec in g.plies:
+            P[at].own, P[at].enemy = rec["own"], rec["enemy"]
+            for a in range(64):
+                P[at].n_visit[a] = int(rec["N"][a])
+            P[at].action, P[at].player, P[at].recorded = rec["action"], rec["pid"], 1
+            at += 1
+    return G, P
+
+
+@pytest.mark.parametrize("tau1,ctt", [(True, 4), (False, 4), (False, 0)])
+def test_writer_matches_python_json(tmp_path, tau1, ctt):
+    pp = mcts.PlayParams(simulation_num_per_move=25, parallel_search_num=4, noise_eps=0.25, change_tau_turn=ctt, c_puct=5,
+                         save_policy_of_tau_1=tau1)
+    games = [mcts.SelfPlayGame(pp, onn.FakeNetAPI(), seed=3, game_id=i).play() for i in range(2)]
+    G, P = to_ctypes(games)
+    path = str(tmp_path / "play_x.json")
+    n = E.write_play_data(path, G, len(games), P, tau1, ctt)
+    expected = []
+    for g in games:
+        expected += [[[int(a), int(b)], [float(x) for x in p], int(z)] for (a, b), p, z in g.records()]
+    assert n == len(expected)
+    text = open(path).read()
+    assert text == json.dumps(expected)
+    # the reference trainer's loader (optimize.py:215-231): for state, policy, z in data -> bit_to_array(state[0], 64)
+    data = json.loads(text)
+    for state, policy, z in data[:50]:
+        own = ob.bit_to_array(state[0], 64).reshape(8, 8)
+        assert own.sum() == bin(state[0]).count("1") and len(policy) == 64 and z in (-1, 0, 1)
+        assert abs(sum(policy) - 1) < 1e-9
+
+
+def test_float_repr_edge_cases(tmp_path):
+    """visit fractions spanning fixed / scientific repr (1/3, 1e-05-ish, 0.0001, integers)."""
+    G = (_cabi.Game * 1)()
+    P = (_cabi.Ply * 4)()
+    counts = [[1, 2] + [0] * 62, [1, 99999] + [0] * 62, [1, 9999] + [0] * 62, [7] + [0] * 63]
+    G[0].n_plies = 4; G[0].black_z = 1
+    for i, c in enumerate(counts):
+        P[i].own, P[i].enemy, P[i].player, P[i].recorded = 0x0000000810000000, 0x0000001008000000, 1, 1
+        for a in range(64):
+            P[i].n_visit[a] = c[a]
+    path = str(tmp_path / "p.json")
+    E.write_play_data(path, G, 1, P, True, 4)
+    data = json.loads(open(path).read())
+    text = open(path).read()
+    for i, c in enumerate(counts):
+        pol = np.array(c) / np.sum(c)
+        assert data[8 * i][1] == list(pol)          # identity symmetry first (agent/player.py:166-179)
+        for v in pol[:2]:
+            assert repr(float(v)) in text
