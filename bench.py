@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- self-play throughput of the B200 engine on BASELINE.json's primary configuration.
+
+A *step* is one engine wave over the resident games: the MCTS tick kernel (consume evaluations, expand,
+back up, decide moves, descend with virtual loss, gather leaves) followed by one launch of the fused
+tcgen05 policy/value tower over the gathered leaf batch.  Workload: ch5 network
+(256 filters x 10 residual blocks, random-init), 4096 concurrent games per GPU, simulation_num_per_move
+= 400, parallel_search_num = 8, c_puct = 5, virtual_loss = 3, noise_eps = 0.25, alpha = 0.5,
+change_tau_turn = 4, thinking_loop = 1, solver off, resignation off.  Games are started in steady state
+(engine warm_start: game phases spread uniformly) so that finished-games/second over a window of K waves is
+the steady-state rate; the plies-based estimate is printed beside it in `config`.
+
+Launch: python bench.py [--gpus N --steps K --warmup W] (N > 1 under torch.distributed.run, one rank per
+GPU).  `--impl reference` times the CPU port of the reference's own self-play worker (oracle/) on the host
+cores instead.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "reversi-alpha-zero_b200"))
+
+FLOP_PER_EXPANSION = 2 * 755_343_616  # ch5 forward, SURVEY 3.2
+PLIES_PER_GAME = 60                   # a full game is 60 plies (turn 0 is decided without search)
+
+MODEL_KW = dict(cnn_filter_num=256, cnn_filter_size=3, res_layer_num=10, value_fc_size=256)
+PLAY_KW = dict(simulation_num_per_move=400, parallel_search_num=8, c_puct=5, virtual_loss=3, noise_eps=0.25,
+               dirichlet_alpha=0.5, change_tau_turn=4, thinking_loop=1, resign_threshold=None,
+               share_mtcs_info_in_self_play=True)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured"
+    except Exception:
+        return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0), "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace(".", "").isdigit())
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = max((int(float(s[1])) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()), default=None)
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_baseline(n_search_plies, processes, torch_threads=1):
+    from oracle import selfplay_cpu
+    r = selfplay_cpu.measure({k: v for k, v in MODEL_KW.items()}, dict(PLAY_KW), n_search_plies=n_search_plies,
+                             processes=processes, torch_threads=torch_threads)
+    games_per_s = r["plies_per_s"] / PLIES_PER_GAME
+    return r, games_per_s
+
+
+def run_reference(args):
+    """CPU port of the reference's self-play worker, one game stream per host core (worker/self_play.py:36-41)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        r, gps = cpu_baseline(n_search_plies=1, processes=cores)
+        last = r
+        if i >= args.warmup:
+            vals.append((gps, r))
+    gps = sum(v for v, _ in vals) / len(vals)
+    eps = sum(r["expansions_per_s"] for _, r in vals) / len(vals)
+    ms = 1e3 * sum(r["wall_s"] for _, r in vals) / len(vals)
+    sample = f"each step: {cores} processes x first searched ply (400 simulations) of one game, torch fp32 CPU forward, 1 thread/process"
+    line = dict(impl="reference", metric="self_play_games_per_sec", value=gps, unit="games/s", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", config=workload_config(args, cores=cores), expansions_per_sec=eps,
+                cpu_baseline=dict(value=gps, unit="games/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=gps, unit="games/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, **extra):
+    c = dict(workload="selfplay ch5 net (256x10, random-init) G=%d games/GPU sims=400 K=8 c_puct=5 vl=3 noise=0.25 tau_turn=4 "
+                      "thinking_loop=1 solver=off resign=off" % args.games,
+             games_per_gpu=args.games, simulation_num_per_move=PLAY_KW["simulation_num_per_move"],
+             l2="leaf batch + per-game trees (>20 GB) exceed L2; weights (23.7 MB fp16) are L2-resident by design",
+             step="one wave = MCTS tick kernel + tcgen05 tower launch over the leaf batch", parallelism=f"dp{args.gpus} (games sharded by rank)")
+    c.update(extra)
+    return c
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=30)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--games", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 8:
+            args.steps, args.warmup = 2, 1  # each step is ~10-20 s of CPU work
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from types import SimpleNamespace
+    from reversi_zero_b200.agent import model as M
+    from reversi_zero_b200 import net as N, engine as E, _cabi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pk, pk_src = peaks()
+
+    mc = M.ModelConfig(**MODEL_KW)
+    net = N.Net(mc, local)
+    # weights: rank 0 builds the random-init blob, ONE NCCL broadcast hands it to every GPU
+    n_blob = M.blob_size(mc)
+    if rank == 0:
+        blob_host = M.weights_to_blob(mc, M.build_random_weights(mc, 0))
+        pinned = torch.from_numpy(blob_host).pin_memory()
+    if world > 1:
+        t_blob = torch.empty(n_blob, dtype=torch.float32, device=f"cuda:{local}")
+        if rank == 0:
+            t_blob.copy_(pinned, non_blocking=True)
+        dist.broadcast(t_blob, src=0)
+        torch.cuda.synchronize()
+        net.load_blob_dev(t_blob)
+    else:
+        net.load_blob(blob_host)
+
+    pp = SimpleNamespace(required_visit_to_decide_action=400, start_rethinking_turn=8, allowed_resign_turn=20,
+                         disable_resignation_rate=0.1, **PLAY_KW)
+
+    def make_engine():
+        cfg = E.engine_cfg_from_play_config(pp, games=args.games, seed=20260922, eval_mode=E.EVAL_NET, first_game_id=rank,
+                                            game_id_stride=world, warm_start=True)
+        return E.Engine(cfg, net, local)
+
+    # ---- device-resident measurement: `value` -------------------------------------------------------------
+    eng = make_engine()
+    eng.run(max_waves=args.warmup)
+    s0 = eng.stats()
+    sampler = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    eng.run(max_waves=args.steps)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    s1 = eng.stats()
+    d = {k: s1[k] - s0[k] for k in s1}
+    run_ms = d["run_ms"]
+    finished_games = eng.poll()
+    plies_per_game = (sum(len(g["plies"]) for g in finished_games) / len(finished_games)) if finished_games else PLIES_PER_GAME
+    eng.close()
+    counts = torch.tensor([d["games_finished"], d["expansions"], d["simulations"], d["plies"], d["nn_launches"] + d["mcts_launches"]],
+                          dtype=torch.float64, device=f"cuda:{local}")
+    tmax = torch.tensor([run_ms, d["nn_ms"], d["mcts_ms"]], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    games, exps, sims, plies, launches = [float(x) for x in counts.tolist()]
+    run_ms, nn_ms, mcts_ms = [float(x) for x in tmax.tolist()]
+    secs = run_ms / 1e3
+    value = games / secs
+    exp_per_s = exps / secs
+
+    # ---- end to end through the public worker path: host weights -> device, waves, harvest, play_data files ----
+    import tempfile
+    from reversi_zero_b200.config import Config
+    from reversi_zero_b200.worker.self_play import SelfPlayWorker
+    tmp = tempfile.mkdtemp(prefix="rz_bench_")
+    cfg = Config(project_dir=tmp, data_dir=os.path.join(tmp, "data"))
+    for k, v in PLAY_KW.items():
+        setattr(cfg.play, k, v)
+    cfg.play.schedule_of_simulation_num_per_move = [(0, PLAY_KW["simulation_num_per_move"])]
+    cfg.play.use_solver_turn = cfg.play.use_solver_turn_in_simulation = 0
+    cfg.play_data.nb_game_in_file = 64
+    cfg.play_data.enable_ggf_data = False
+    cfg.b200.games_per_gpu = args.games
+    cfg.resource.create_directories()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    net2 = N.Net(mc, local)
+    if rank == 0:
+        net2.load_blob(pinned.numpy())           # H2D of the weights from pinned host memory, inside the timed region
+    elif world > 1:
+        net2.load_blob_dev(t_blob)
+    worker = SelfPlayWorker(cfg, net=net2, device=local, rank=rank, world_size=world)
+    ecfg = E.engine_cfg_from_play_config(pp, games=args.games, seed=20260923, eval_mode=E.EVAL_NET, first_game_id=rank,
+                                         game_id_stride=world, warm_start=True)
+    worker.engine = E.Engine(ecfg, net2, local)
+    worker.engine.run(max_waves=args.steps)
+    n_e2e = worker._harvest()
+    worker._flush_files(force=True)
+    torch.cuda.synchronize()
+    e2e_secs = time.perf_counter() - t0
+    file_bytes = sum(os.path.getsize(p) for p in worker.files_written)
+    d2h = n_e2e * (48 + 60 * 288) + (args.steps // 8 + 1) * (80 + 2 * args.games)
+    e2e_t = torch.tensor([float(n_e2e), e2e_secs], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        g_ = e2e_t.clone(); dist.all_reduce(g_, op=dist.ReduceOp.SUM)
+        m_ = e2e_t.clone(); dist.all_reduce(m_, op=dist.ReduceOp.MAX)
+        n_e2e_all, e2e_secs = float(g_[0]), float(m_[1])
+    else:
+        n_e2e_all = float(n_e2e)
+    worker.engine.close()
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    e2e_value = n_e2e_all / e2e_secs
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the tcgen05 tower): algorithmic flop / device time of its launches ----
+    nn_launches = d["nn_launches"]
+    rank_exps = d["expansions"]
+    achieved = rank_exps * FLOP_PER_EXPANSION / (d["nn_ms"] / 1e3) / 1e12 if d["nn_ms"] > 0 else 0.0
+    peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1400.0))  # kernel timed inside a long step
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("tower_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic,
+                    peak_source=f"{pk_src} bf16_tflops_sustained", kernel="net_tower_kernel",
+                    launches=nn_launches, avg_launch_ms=d["nn_ms"] / max(1, nn_launches),
+                    mean_leaf_batch=rank_exps / max(1, nn_launches), share_of_step=d["nn_ms"] / max(1e-9, d["run_ms"]),
+                    mcts_tick_share_of_step=d["mcts_ms"] / max(1e-9, d["run_ms"]))
+
+    cb = None
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        r, gps = cpu_baseline(n_search_plies=1, processes=cores)
+        cb = dict(value=gps, unit="games/s", cores=cores, kind="port",
+                  sample=f"{cores} processes x first searched ply (400 sims) of one game each; {r['expansions']} expansions in {r['wall_s']:.1f} s",
+                  expansions_per_sec=r["expansions_per_s"], mean_nn_batch=r["mean_batch"])
+
+    line = dict(metric="self_play_games_per_sec", value=value, unit="games/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=run_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16 operands / f32 accumulate",
+                data="synthetic (random-init ch5 weights, self-generated games)",
+                config=workload_config(args, games_finished_in_window=games, plies_decided=plies,
+                                       games_per_sec_plies_based=plies / secs / plies_per_game, plies_per_game_observed=plies_per_game,
+                                       timing="CUDA events on the engine stream, first to last wave; max over ranks"),
+                node_expansions_per_sec=exp_per_s, simulations_per_sec=sims / secs,
+                roofline=roofline, cpu_baseline=cb, clocks=clocks,
+                e2e=dict(value=e2e_value, unit="games/s", h2d_bytes_per_step=int(n_blob * 4 / args.steps), d2h_bytes_per_step=int(d2h / args.steps),
+                         play_data_bytes_written=file_bytes, games=n_e2e_all, seconds=e2e_secs,
+                         what="host weight blob -> device + pack, engine create, K waves, harvest, play_*.json written"),
+                gpu_launches=int(launches))
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

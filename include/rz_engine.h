@@ -148,6 +148,11 @@ typedef struct rz_engine_cfg {
     int32_t eval_mode;              /* RZ_EVAL_* */
     int32_t net_impl;               /* RZ_NET_IMPL_* */
     int32_t max_plies;              /* per-game ply log capacity, 0 => 64 */
+    int32_t warm_start;             /* 1: the FIRST game of every slot begins after a random number (0..57) of
+                                       random legal plies, so a fresh engine is in steady state (game phases
+                                       spread uniformly) instead of all slots marching in lock step; those
+                                       pre-played plies are not searched and not recorded */
+    int32_t reserved;
     float c_puct;                   /* :135 */
     float noise_eps;                /* :136 */
     float dirichlet_alpha;          /* :137 */
@@ -196,6 +201,8 @@ typedef struct rz_stats {
     uint64_t plies;
     uint64_t nn_launches, mcts_launches; /* kernels launched by the engine */
     uint64_t max_nodes_used, max_edges_used;
+    double nn_ms, mcts_ms; /* device time (CUDA events on the engine's stream) spent in the two kernel families */
+    double run_ms;         /* device time from the first to the last wave of each rz_engine_run call, accumulated */
 } rz_stats;
 
 int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net /* may be NULL for RZ_EVAL_FAKE */, int device,
@@ -211,10 +218,16 @@ int rz_engine_stats(rz_engine* e, rz_stats* out);
 /* change the per-move simulation count for games started from now on
  * (SelfPlayWorker.decide_simulation_num_per_move, worker/self_play.py:262-272). */
 int rz_engine_set_simulation_num(rz_engine* e, int32_t sims);
-/* test hook: search one root position in every slot (no game loop) and return the root statistics of
- * slot `slot`: n_visit[64], w[64].  Used by the parity tests against oracle/mcts.py. */
-int rz_engine_search_root(rz_engine* e, uint64_t own, uint64_t enemy, int player, int slot, int32_t* n_visit,
-                          float* w_sum);
+/* update the resignation rule for decisions taken from now on (SelfPlayWorker's threshold auto-tuner,
+ * worker/self_play.py:250-260). */
+int rz_engine_set_resign_threshold(rz_engine* e, int use_resign_threshold, float resign_threshold);
+/* single-position search (ReversiPlayer.action outside the self-play loop: evaluate.py, nboard.py, GUI; also the
+ * parity-test hook): every slot searches (own, enemy) with `player` to move for simulation_num_per_move
+ * simulations; returns the root statistics of slot `slot`: n_visit[64], w_sum[64] (mover's frame).
+ * keep_tree != 0 keeps the slot's transposition table from earlier calls (the reference's MCTSInfo that
+ * persists across the moves of a game, agent/player.py:44-47); 0 starts from an empty table. */
+int rz_engine_search_root(rz_engine* e, uint64_t own, uint64_t enemy, int player, int slot, int keep_tree,
+                          int32_t* n_visit, float* w_sum);
 
 /* ------------------------------------------------------------------------------------------------
  * play_data writer -- the reference's output contract (worker/self_play.py:180-194,

@@ -101,7 +101,7 @@ struct Status {
 
 struct DevCfg {
     int G, S, K, vl, change_tau_turn, thinking_loop, required_visit, start_rethinking_turn, allowed_resign_turn;
-    int use_resign, share, max_plies;
+    int use_resign, share, max_plies, warm_start;
     float c_puct, noise_eps, alpha, resign_threshold, disable_resignation_rate;
     u64 seed, first_game_id, game_id_stride, max_games;
     uint32_t nodes_cap, edges_cap, hash_cap;  // per slot (hash_cap is a power of two)
@@ -409,6 +409,22 @@ struct Ctx {
         sl.enable_resign = (uint8_t)((double)c.disable_resignation_rate <= u01(draw(c.seed, sl.game_id, 0, P_GAME, 0).x));
         atomicAdd(&p.status->games_started, 1ULL);
         sl.phase = PH_DECIDE;  // turn 0: bypass_first_move decides without a search
+        if (c.warm_start && sl.games_played == 1) {
+            // steady-state start: advance this slot's first game by a random number of random legal plies
+            const U4 r0 = draw(c.seed, sl.game_id, 1, P_GAME, 0);
+            const int pre = (int)(u01(r0.x) * 58.0);
+            for (int i = 0; i < pre && !sl.env.done; ++i) {
+                const bool b = sl.env.next_player == 1;
+                const u64 legal = find_correct_moves(b ? sl.env.black : sl.env.white, b ? sl.env.white : sl.env.black);
+                const U4 r = draw(c.seed, sl.game_id, 2 + (uint32_t)i, P_GAME, 0);
+                env_step(sl.env, nth_set_bit(legal, (int)(u01(r.x) * (double)popc64(legal))));
+            }
+            if (sl.env.done) env_reset(sl.env);
+            else if (sl.env.turn > 0) {
+                const bool b = sl.env.next_player == 1;
+                begin_search(b ? sl.env.black : sl.env.white, b ? sl.env.white : sl.env.black, sl.env.next_player);
+            }
+        }
     }
 
     __device__ void finish_game() {
@@ -594,15 +610,18 @@ __global__ void init_slots_kernel(const DevCfg c, const DevPtrs p) {
 }
 
 // test hook: every slot searches the same root once (no game loop)
-__global__ void setup_search_root_kernel(const DevCfg c, const DevPtrs p, u64 own, u64 enemy, int pid) {
+__global__ void setup_search_root_kernel(const DevCfg c, const DevPtrs p, u64 own, u64 enemy, int pid, int keep_tree) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= c.G) return;
     Ctx x(c, p, s);
     Slot& sl = x.sl;
     sl.game_id = c.first_game_id + (u64)s * c.game_id_stride;
-    sl.gen = sl.gen + 1;
-    if (sl.gen >= 4096) { for (uint32_t i = 0; i < c.hash_cap; ++i) x.hash[i] = 0; sl.gen = 1; }
-    sl.n_nodes = 0; sl.n_edges = 0; sl.n_expand = 0; sl.n_rootsel = 0; sl.n_sims = 0; sl.ply = 0; sl.tl = 0;
+    if (!keep_tree || sl.gen == 0) {
+        sl.gen = sl.gen + 1;
+        if (sl.gen >= 4096) { for (uint32_t i = 0; i < c.hash_cap; ++i) x.hash[i] = 0; sl.gen = 1; }
+        sl.n_nodes = 0; sl.n_edges = 0; sl.n_expand = 0; sl.n_rootsel = 0; sl.n_sims = 0;
+    }
+    sl.ply = 0; sl.tl = 0;
     for (int k = 0; k < c.K; ++k) x.desc[k].status = D_FREE;
     env_update(sl.env, pid == 1 ? own : enemy, pid == 1 ? enemy : own, pid);
     x.begin_search(own, enemy, pid);
@@ -643,7 +662,23 @@ struct rz_engine {
     uint64_t waves, nn_launches, mcts_launches;
     uint64_t finished_total;
     std::deque<FinishedGame> queue;
+    // device timing: 3 events per queued wave (before tick, between tick and evaluation, after evaluation)
+    cudaEvent_t ev[3 * 8];
+    cudaEvent_t ev_run[2];
+    int ev_used;
+    double nn_ms, mcts_ms, run_ms;
 };
+
+static int collect_timing(rz_engine* e) {  // call after the stream has been synchronised
+    for (int i = 0; i < e->ev_used; ++i) {
+        float a = 0.f, b = 0.f;
+        RZ_CUDA_TRY(cudaEventElapsedTime(&a, e->ev[3 * i], e->ev[3 * i + 1]));
+        RZ_CUDA_TRY(cudaEventElapsedTime(&b, e->ev[3 * i + 1], e->ev[3 * i + 2]));
+        e->mcts_ms += a; e->nn_ms += b;
+    }
+    e->ev_used = 0;
+    return RZ_OK;
+}
 
 static int dev_alloc(rz_engine* e, void** ptr, size_t bytes, bool zero) {
     cudaError_t ce = cudaMalloc(ptr, bytes);
@@ -681,10 +716,13 @@ static int drain_mailboxes(rz_engine* e) {
 
 static int launch_wave(rz_engine* e) {
     const DevCfg& c = e->dc;
+    const bool timed = e->ev_used < 8;
+    if (timed) RZ_CUDA_TRY(cudaEventRecord(e->ev[3 * e->ev_used], e->stream));
     RZ_CUDA_TRY(cudaMemsetAsync(e->dp.batch_count, 0, sizeof(uint32_t), e->stream));
     tick_kernel<<<(c.G + kTickThreads - 1) / kTickThreads, kTickThreads, 0, e->stream>>>(c, e->dp);
     RZ_LAUNCH_CHECK();
     e->mcts_launches++;
+    if (timed) RZ_CUDA_TRY(cudaEventRecord(e->ev[3 * e->ev_used + 1], e->stream));
     if (e->cfg.eval_mode == RZ_EVAL_FAKE) {
         fake_eval_kernel<<<num_sms() * 4, 256, 0, e->stream>>>(e->dp.batch_own, e->dp.batch_enemy, e->dp.batch_count, e->dp.policy, e->dp.value);
         RZ_LAUNCH_CHECK();
@@ -694,6 +732,7 @@ static int launch_wave(rz_engine* e) {
                                    (size_t)c.G * c.K, e->cfg.net_impl, e->stream));
         e->nn_launches++;
     }
+    if (timed) { RZ_CUDA_TRY(cudaEventRecord(e->ev[3 * e->ev_used + 2], e->stream)); e->ev_used++; }
     e->waves++;
     return RZ_OK;
 }
@@ -701,6 +740,7 @@ static int launch_wave(rz_engine* e) {
 static int read_status(rz_engine* e) {
     RZ_CUDA_TRY(cudaMemcpyAsync(e->h_status, e->dp.status, sizeof(Status), cudaMemcpyDeviceToHost, e->stream));
     RZ_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    RZ_TRY(collect_timing(e));
     if (e->h_status->error != 0) {
         set_error("rz_engine: device-side failure %d (%s)", e->h_status->error,
                   e->h_status->error == RZ_ECAPACITY ? "node/edge/ply arena overflow" : "inconsistent search state");
@@ -725,11 +765,15 @@ int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net, int device, rz_engin
     e->cfg = *cfg; e->net = net; e->device = device; e->n_arena = 0;
     e->waves = e->nn_launches = e->mcts_launches = e->finished_total = 0;
     e->h_status = nullptr; e->h_flags = nullptr; e->stream = nullptr;
+    e->ev_used = 0; e->nn_ms = e->mcts_ms = e->run_ms = 0.0;
+    for (int i = 0; i < 24; ++i) e->ev[i] = nullptr;
+    e->ev_run[0] = e->ev_run[1] = nullptr;
     DevCfg& c = e->dc;
     c.G = cfg->games; c.S = cfg->simulation_num_per_move; c.K = cfg->parallel_search_num; c.vl = cfg->virtual_loss;
     c.change_tau_turn = cfg->change_tau_turn; c.thinking_loop = cfg->thinking_loop; c.required_visit = cfg->required_visit_to_decide_action;
     c.start_rethinking_turn = cfg->start_rethinking_turn; c.allowed_resign_turn = cfg->allowed_resign_turn;
     c.use_resign = cfg->use_resign_threshold; c.share = cfg->share_mtcs_info; c.max_plies = cfg->max_plies > 0 ? cfg->max_plies : 64;
+    c.warm_start = cfg->warm_start;
     c.c_puct = cfg->c_puct; c.noise_eps = cfg->noise_eps; c.alpha = cfg->dirichlet_alpha; c.resign_threshold = cfg->resign_threshold;
     c.disable_resignation_rate = cfg->disable_resignation_rate;
     c.seed = cfg->seed; c.first_game_id = cfg->first_game_id; c.game_id_stride = cfg->game_id_stride; c.max_games = cfg->max_games;
@@ -762,6 +806,10 @@ int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net, int device, rz_engin
     if (!rc) rc = dev_alloc(e, (void**)&p.value, (B + 2) * sizeof(float), true);
     if (!rc && cudaMallocHost((void**)&e->h_status, sizeof(Status)) != cudaSuccess) { set_error("cudaMallocHost failed"); rc = RZ_ENOMEM; }
     if (!rc && cudaMallocHost((void**)&e->h_flags, G * 2) != cudaSuccess) { set_error("cudaMallocHost failed"); rc = RZ_ENOMEM; }
+    for (int i = 0; i < 24 && !rc; ++i)
+        if (cudaEventCreate(&e->ev[i]) != cudaSuccess) { set_error("cudaEventCreate failed"); rc = RZ_ECUDA; }
+    for (int i = 0; i < 2 && !rc; ++i)
+        if (cudaEventCreate(&e->ev_run[i]) != cudaSuccess) { set_error("cudaEventCreate failed"); rc = RZ_ECUDA; }
     if (rc) { rz_engine_destroy(e); return rc; }
     init_slots_kernel<<<(c.G + 127) / 128, 128, 0, e->stream>>>(c, p);
     ce = cudaStreamSynchronize(e->stream);
@@ -777,6 +825,8 @@ int rz_engine_destroy(rz_engine* e) {
     for (int i = 0; i < e->n_arena; ++i) cudaFree(e->arena[i]);
     if (e->h_status) cudaFreeHost(e->h_status);
     if (e->h_flags) cudaFreeHost(e->h_flags);
+    for (int i = 0; i < 24; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    for (int i = 0; i < 2; ++i) if (e->ev_run[i]) cudaEventDestroy(e->ev_run[i]);
     if (e->stream) cudaStreamDestroy(e->stream);
     cudaGetLastError();
     delete e;
@@ -788,6 +838,8 @@ int rz_engine_run(rz_engine* e, uint64_t finished_target, uint64_t max_waves) {
     RZ_CUDA_TRY(cudaSetDevice(e->device));
     const uint64_t wave0 = e->waves;
     const int kCheck = 8;  // waves queued between host checks
+    RZ_CUDA_TRY(cudaEventRecord(e->ev_run[0], e->stream));
+    int rc_loop = RZ_OK;
     while (true) {
         if (e->finished_total >= finished_target && finished_target > 0) break;
         if (max_waves && e->waves - wave0 >= max_waves) break;
@@ -801,6 +853,12 @@ int rz_engine_run(rz_engine* e, uint64_t finished_target, uint64_t max_waves) {
             break;
         }
     }
+    (void)rc_loop;
+    RZ_CUDA_TRY(cudaEventRecord(e->ev_run[1], e->stream));
+    RZ_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    float ms = 0.f;
+    RZ_CUDA_TRY(cudaEventElapsedTime(&ms, e->ev_run[0], e->ev_run[1]));
+    e->run_ms += ms;
     return RZ_OK;
 }
 
@@ -830,6 +888,8 @@ int rz_engine_stats(rz_engine* e, rz_stats* out) {
     out->games_started = s.games_started; out->games_finished = s.games_finished; out->expansions = s.expansions;
     out->simulations = s.simulations; out->waves = e->waves; out->plies = s.plies; out->nn_launches = e->nn_launches;
     out->mcts_launches = e->mcts_launches; out->max_nodes_used = s.max_nodes; out->max_edges_used = s.max_edges;
+    RZ_TRY(collect_timing(e));
+    out->nn_ms = e->nn_ms; out->mcts_ms = e->mcts_ms; out->run_ms = e->run_ms;
     return RZ_OK;
 }
 
@@ -842,11 +902,21 @@ int rz_engine_set_simulation_num(rz_engine* e, int32_t sims) {
     return RZ_OK;
 }
 
-int rz_engine_search_root(rz_engine* e, uint64_t own, uint64_t enemy, int player, int slot, int32_t* n_visit, float* w_sum) {
+int rz_engine_set_resign_threshold(rz_engine* e, int use_resign_threshold, float resign_threshold) {
+    RZ_REQUIRE(e, "rz_engine_set_resign_threshold: null engine");
+    e->dc.use_resign = use_resign_threshold ? 1 : 0;
+    e->dc.resign_threshold = resign_threshold;
+    e->cfg.use_resign_threshold = e->dc.use_resign;
+    e->cfg.resign_threshold = resign_threshold;
+    return RZ_OK;
+}
+
+int rz_engine_search_root(rz_engine* e, uint64_t own, uint64_t enemy, int player, int slot, int keep_tree, int32_t* n_visit,
+                          float* w_sum) {
     RZ_REQUIRE(e && n_visit && w_sum && (player == 1 || player == 2) && slot >= 0 && slot < e->dc.G, "rz_engine_search_root: bad argument");
     RZ_CUDA_TRY(cudaSetDevice(e->device));
     RZ_CUDA_TRY(cudaMemsetAsync(e->dp.status, 0, sizeof(Status), e->stream));
-    setup_search_root_kernel<<<(e->dc.G + 127) / 128, 128, 0, e->stream>>>(e->dc, e->dp, own, enemy, player);
+    setup_search_root_kernel<<<(e->dc.G + 127) / 128, 128, 0, e->stream>>>(e->dc, e->dp, own, enemy, player, keep_tree);
     RZ_LAUNCH_CHECK();
     for (int it = 0; it < 1000000; ++it) {
         for (int i = 0; i < 8; ++i) RZ_TRY(launch_wave(e));

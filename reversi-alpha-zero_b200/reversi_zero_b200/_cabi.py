@@ -31,7 +31,7 @@ class EngineCfg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "games", "simulation_num_per_move", "parallel_search_num", "virtual_loss", "change_tau_turn", "thinking_loop",
         "required_visit_to_decide_action", "start_rethinking_turn", "allowed_resign_turn", "use_resign_threshold",
-        "share_mtcs_info", "eval_mode", "net_impl", "max_plies")] + [(n, C.c_float) for n in (
+        "share_mtcs_info", "eval_mode", "net_impl", "max_plies", "warm_start", "reserved")] + [(n, C.c_float) for n in (
             "c_puct", "noise_eps", "dirichlet_alpha", "resign_threshold", "disable_resignation_rate")] + [
         (n, C.c_uint64) for n in ("seed", "first_game_id", "game_id_stride", "max_games")]
 
@@ -51,7 +51,8 @@ class Game(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("games_started", "games_finished", "expansions", "simulations", "waves",
-                                          "plies", "nn_launches", "mcts_launches", "max_nodes_used", "max_edges_used")]
+                                          "plies", "nn_launches", "mcts_launches", "max_nodes_used", "max_edges_used")] + [
+        ("nn_ms", C.c_double), ("mcts_ms", C.c_double), ("run_ms", C.c_double)]
 
 
 # name -> (restype, argtypes); every symbol include/rz_engine.h declares
@@ -86,7 +87,8 @@ SIGNATURES = {
     "rz_engine_poll": (C.c_int, [vp, C.POINTER(Game), sz, C.POINTER(sz), C.POINTER(Ply), sz, C.POINTER(sz)]),
     "rz_engine_stats": (C.c_int, [vp, C.POINTER(Stats)]),
     "rz_engine_set_simulation_num": (C.c_int, [vp, C.c_int32]),
-    "rz_engine_search_root": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int, i32p, f32p]),
+    "rz_engine_set_resign_threshold": (C.c_int, [vp, C.c_int, C.c_float]),
+    "rz_engine_search_root": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, i32p, f32p]),
     "rz_write_play_data": (C.c_int, [C.c_char_p, C.POINTER(Game), sz, C.POINTER(Ply), C.c_int, C.c_int, C.POINTER(sz)]),
 }
 

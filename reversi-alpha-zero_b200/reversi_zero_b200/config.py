@@ -1,0 +1,146 @@
+"""Configuration tree with the reference's field names and defaults (config.py:15-193) so that the
+reference's YAML files (config/*.yml) and its own ``Config`` objects drive the B200 engine unchanged.
+Only the sections the self-play path reads are modelled; any object exposing the same attributes
+(e.g. the reference's ``Config`` built by moke_config) is accepted everywhere in this package.
+
+Engine-specific knobs live in ``Config.b200`` (not present in the reference): concurrent games per
+GPU, seed, network implementation.
+"""
+import os
+
+
+class _Section:
+    def update(self, d):
+        for k, v in (d or {}).items():
+            cur = getattr(self, k, None)
+            if isinstance(v, dict) and isinstance(cur, _Section):
+                cur.update(v)
+            else:
+                setattr(self, k, v)
+        return self
+
+
+class Options(_Section):
+    new = False
+
+
+class ResourceConfig(_Section):
+    """config.py:34-65"""
+
+    def __init__(self, project_dir=None, data_dir=None):
+        self.project_dir = project_dir or os.environ.get("PROJECT_DIR", os.getcwd())
+        self.data_dir = data_dir or os.environ.get("DATA_DIR", os.path.join(self.project_dir, "data"))
+        self.model_dir = os.environ.get("MODEL_DIR", os.path.join(self.data_dir, "model"))
+        self.model_best_config_path = os.path.join(self.model_dir, "model_best_config.json")
+        self.model_best_weight_path = os.path.join(self.model_dir, "model_best_weight.h5")
+        self.next_generation_model_dir = os.path.join(self.model_dir, "next_generation")
+        self.next_generation_model_dirname_tmpl = "model_%s"
+        self.next_generation_model_config_filename = "model_config.json"
+        self.next_generation_model_weight_filename = "model_weight.h5"
+        self.play_data_dir = os.path.join(self.data_dir, "play_data")
+        self.play_data_filename_tmpl = "play_%s.json"
+        self.self_play_ggf_data_dir = os.path.join(self.data_dir, "self_play-ggf")
+        self.ggf_filename_tmpl = "self_play-%s.ggf"
+        self.log_dir = os.path.join(self.project_dir, "logs")
+        self.main_log_path = os.path.join(self.log_dir, "main.log")
+        self.tensorboard_log_dir = os.path.join(self.log_dir, "tensorboard")
+        self.self_play_log_dir = os.path.join(self.tensorboard_log_dir, "self_play")
+        self.force_learing_rate_file = os.path.join(self.data_dir, ".force-lr")
+        self.force_simulation_num_file = os.path.join(self.data_dir, ".force-sim")
+        self.self_play_game_idx_file = os.path.join(self.data_dir, ".self-play-game-idx")
+        # engine-side weight hand-off (float32 blob in the layout of include/rz_engine.h)
+        self.model_best_blob_path = os.path.join(self.model_dir, "model_best_weight.rzblob.npy")
+
+    def create_directories(self):
+        for d in (self.project_dir, self.data_dir, self.model_dir, self.play_data_dir, self.log_dir,
+                  self.next_generation_model_dir, self.self_play_log_dir, self.self_play_ggf_data_dir):
+            os.makedirs(d, exist_ok=True)
+
+
+class ModelConfig(_Section):
+    """config.py:187-193"""
+
+    def __init__(self):
+        self.cnn_filter_num = 256
+        self.cnn_filter_size = 3
+        self.res_layer_num = 10
+        self.l2_reg = 1e-4
+        self.value_fc_size = 256
+
+
+class PlayConfig(_Section):
+    """config.py:128-166"""
+
+    def __init__(self):
+        self.simulation_num_per_move = 200
+        self.share_mtcs_info_in_self_play = True
+        self.reset_mtcs_info_per_game = 1
+        self.thinking_loop = 10
+        self.required_visit_to_decide_action = 400
+        self.start_rethinking_turn = 8
+        self.c_puct = 1
+        self.noise_eps = 0.25
+        self.dirichlet_alpha = 0.5
+        self.change_tau_turn = 4
+        self.virtual_loss = 3
+        self.prediction_queue_size = 16
+        self.parallel_search_num = 8
+        self.prediction_worker_sleep_sec = 0.0001
+        self.wait_for_expanding_sleep_sec = 0.00001
+        self.resign_threshold = -0.9
+        self.allowed_resign_turn = 20
+        self.disable_resignation_rate = 0.1
+        self.false_positive_threshold = 0.05
+        self.resign_threshold_delta = 0.01
+        self.policy_decay_turn = 60
+        self.policy_decay_power = 3
+        self.use_solver_turn = 50
+        self.use_solver_turn_in_simulation = 50
+        self.schedule_of_simulation_num_per_move = [(0, 8), (300, 50), (2000, 200)]
+        self.use_newest_next_generation_model = True
+
+
+class PlayDataConfig(_Section):
+    """config.py:116-125"""
+
+    def __init__(self):
+        self.multi_process_num = 16
+        self.nb_game_in_file = 2
+        self.max_file_num = 800
+        self.save_policy_of_tau_1 = True
+        self.enable_ggf_data = True
+        self.nb_game_in_ggf_file = 100
+        self.drop_draw_game_rate = 0
+
+
+class B200Config(_Section):
+    """Engine knobs that have no counterpart in the reference."""
+
+    def __init__(self):
+        self.games_per_gpu = 4096   # concurrent game slots (replaces play_data.multi_process_num worker processes)
+        self.seed = 20260922
+        self.net_impl = 0           # RZ_NET_IMPL_AUTO
+        self.weight_seed = 0        # random-init seed used when no weights exist (`--new`, agent/api.py:112-114)
+
+
+class Config(_Section):
+    def __init__(self, project_dir=None, data_dir=None):
+        self.type = "default"
+        self.opts = Options()
+        self.resource = ResourceConfig(project_dir, data_dir)
+        self.model = ModelConfig()
+        self.play = PlayConfig()
+        self.play_data = PlayDataConfig()
+        self.b200 = B200Config()
+
+
+def create_config(d=None, project_dir=None, data_dir=None):
+    """Overlay a dict (e.g. yaml.safe_load of the reference's config/*.yml) on the defaults; unknown
+    sections (trainer, eval, gui ...) are kept as plain attributes and ignored by the self-play path."""
+    return Config(project_dir, data_dir).update(d or {})
+
+
+def load_yaml(path, **kw):
+    import yaml
+    with open(path, "rt") as f:
+        return create_config(yaml.safe_load(f), **kw)

@@ -10,7 +10,7 @@ EVAL_NET, EVAL_FAKE = 0, 1
 
 
 def engine_cfg_from_play_config(pc, pdc=None, games=1024, seed=0, eval_mode=EVAL_NET, net_impl=0, first_game_id=0,
-                                game_id_stride=1, max_games=0):
+                                game_id_stride=1, max_games=0, warm_start=False):
     """Build an rz_engine_cfg from objects with the reference's PlayConfig / PlayDataConfig fields
     (config.py:116-166)."""
     cfg = _cabi.EngineCfg()
@@ -28,6 +28,7 @@ def engine_cfg_from_play_config(pc, pdc=None, games=1024, seed=0, eval_mode=EVAL
     cfg.eval_mode = eval_mode
     cfg.net_impl = net_impl
     cfg.max_plies = 64
+    cfg.warm_start = 1 if warm_start else 0
     cfg.c_puct = float(pc.c_puct)
     cfg.noise_eps = float(pc.noise_eps)
     cfg.dirichlet_alpha = float(pc.dirichlet_alpha)
@@ -82,15 +83,20 @@ class Engine:
     def stats(self):
         s = _cabi.Stats()
         _cabi.check(_cabi.lib().rz_engine_stats(self._h, C.byref(s)), "rz_engine_stats")
-        return {n: int(getattr(s, n)) for n, _ in _cabi.Stats._fields_}
+        return {n: (float if t is C.c_double else int)(getattr(s, n)) for n, t in _cabi.Stats._fields_}
 
     def set_simulation_num(self, sims):
         _cabi.check(_cabi.lib().rz_engine_set_simulation_num(self._h, int(sims)), "rz_engine_set_simulation_num")
 
-    def search_root(self, own, enemy, player, slot=0):
+    def set_resign_threshold(self, threshold):
+        _cabi.check(_cabi.lib().rz_engine_set_resign_threshold(self._h, 0 if threshold is None else 1,
+                                                               0.0 if threshold is None else float(threshold)),
+                    "rz_engine_set_resign_threshold")
+
+    def search_root(self, own, enemy, player, slot=0, keep_tree=False):
         n = np.zeros(64, np.int32)
         w = np.zeros(64, np.float32)
-        _cabi.check(_cabi.lib().rz_engine_search_root(self._h, own, enemy, player, slot, n.ctypes.data_as(_cabi.i32p),
+        _cabi.check(_cabi.lib().rz_engine_search_root(self._h, own, enemy, player, slot, int(keep_tree), n.ctypes.data_as(_cabi.i32p),
                                                        w.ctypes.data_as(_cabi.f32p)), "rz_engine_search_root")
         return n, w
 

@@ -1,0 +1,267 @@
+"""Mirror of the reference's self-play worker (worker/self_play.py) on the B200 engine.
+
+``start(config)`` / ``SelfPlayWorker(config, env, api, shared_var, worker_index).start()`` keep the
+reference's entry points (manager.py:51-53, worker/self_play.py:28-41,64-93) and output contract:
+``play_%Y%m%d-%H%M%S.%f.json`` files of ``[[own, enemy], [64 floats], z]`` records (self_play.py:180-194),
+``self_play-*.ggf`` game records (:196-207), pruning to ``max_file_num`` files (:209-217), the
+``.self-play-game-idx`` counter (:35,136-137), the simulation-count schedule / ``.force-sim`` override
+(:262-272), draw dropping (:182) and the resignation-threshold auto-tuner (:219-260).
+
+What differs by design: the reference forks ``multi_process_num`` Python workers that play one game
+each and talk to a Keras server through pipes; here ONE process per GPU drives ``b200.games_per_gpu``
+concurrent games that live entirely on the device (csrc/rz_engine.cu), and finished games are harvested
+in batches.  Across GPUs the game-id space is strided by rank and every rank writes its own files
+(SURVEY 8(e)); the only collective is the weight broadcast.
+"""
+import os
+import random
+import time
+from datetime import datetime
+from logging import getLogger
+
+import numpy as np
+
+from .. import _cabi
+from ..agent import model as M
+from ..engine import Engine, engine_cfg_from_play_config, write_play_data, EVAL_NET
+from ..lib.ggf import convert_action_to_move, make_ggf_string
+from ..net import Net
+
+logger = getLogger(__name__)
+
+
+def start(config):
+    return SelfPlayWorker(config).start()
+
+
+def read_as_int(filename):
+    """lib/file_util.py:4-13"""
+    if os.path.exists(filename):
+        try:
+            with open(filename, "rt") as f:
+                ret = int(str(f.read()).strip())
+                if ret:
+                    return ret
+        except ValueError:
+            pass
+
+
+def _b200(config):
+    from ..config import B200Config
+    return getattr(config, "b200", None) or B200Config()
+
+
+def load_or_build_weights(config, net):
+    """agent/api.py:102-115 load_model: best weights if present, else build() + save_as_best (``--new``).
+    The engine-side hand-off file is a float32 .npy blob (h5 import from the Keras trainer: SURVEY 8(f).1)."""
+    rc = config.resource
+    path = getattr(rc, "model_best_blob_path", os.path.join(rc.model_dir, "model_best_weight.rzblob.npy"))
+    if not getattr(config.opts, "new", False) and os.path.exists(path):
+        blob = np.load(path)
+        logger.debug(f"loading weights from {path}")
+    else:
+        blob = M.weights_to_blob(config.model, M.build_random_weights(config.model, _b200(config).weight_seed))
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        np.save(path, blob)
+        logger.debug(f"built random-init weights, saved to {path}")
+    net.load_blob(blob)
+    return blob
+
+
+class SelfPlayWorker:
+    def __init__(self, config, env=None, api=None, shared_var=None, worker_index=0, net=None, device=0, rank=0,
+                 world_size=1):
+        """env / api / shared_var are accepted for signature compatibility with the reference
+        (worker/self_play.py:65-86); games run on the device and ``net`` (a ``reversi_zero_b200.net.Net``)
+        takes the place of the API client."""
+        self.config = config
+        self.env = env
+        self.api = api
+        self.shared_var = shared_var
+        self.worker_index = worker_index
+        self.net = net
+        self.device = device
+        self.rank, self.world_size = rank, world_size
+        self.buffer_games = []        # (Game header copy, [Ply copies]) kept for the next play_data file
+        self.ggf_lines = []
+        self.false_positive_count_of_resign = 0
+        self.resign_test_game_count = 0
+        self.engine = None
+        self.local_idx = 0
+        self.game_idx = 0
+        self.files_written = []
+
+    # -- reference helpers ---------------------------------------------------------------------------------
+    def decide_simulation_num_per_move(self, idx):
+        """worker/self_play.py:262-272"""
+        ret = read_as_int(self.config.resource.force_simulation_num_file)
+        if ret:
+            return ret
+        for min_idx, num in self.config.play.schedule_of_simulation_num_per_move:
+            if idx >= min_idx:
+                ret = num
+        return ret
+
+    @property
+    def false_positive_rate(self):
+        if self.resign_test_game_count == 0:
+            return 0
+        return self.false_positive_count_of_resign / self.resign_test_game_count
+
+    def check_and_update_resignation_threshold(self):
+        """worker/self_play.py:250-260"""
+        pc = self.config.play
+        if self.resign_test_game_count < 100 or pc.resign_threshold is None:
+            return
+        old = pc.resign_threshold
+        if self.false_positive_rate >= pc.false_positive_threshold:
+            pc.resign_threshold -= pc.resign_threshold_delta
+        else:
+            pc.resign_threshold += pc.resign_threshold_delta
+        logger.debug(f"update resign_threshold: {old} -> {pc.resign_threshold}")
+        self.false_positive_count_of_resign = 0
+        self.resign_test_game_count = 0
+        self.engine.set_resign_threshold(pc.resign_threshold)
+
+    # -- engine plumbing ------------------------------------------------------------------------------------
+    def _make_engine(self):
+        cfg, b = self.config, _b200(self.config)
+        rc = cfg.resource
+        rc.create_directories() if hasattr(rc, "create_directories") else None
+        if self.net is None:
+            self.net = Net(cfg.model, self.device)
+            load_or_build_weights(cfg, self.net)
+        self.game_idx = read_as_int(rc.self_play_game_idx_file) or 0
+        sims = self.decide_simulation_num_per_move(self.game_idx)
+        cfg.play.simulation_num_per_move = sims
+        ecfg = engine_cfg_from_play_config(cfg.play, games=b.games_per_gpu, seed=b.seed, eval_mode=EVAL_NET, net_impl=b.net_impl,
+                                           first_game_id=self.game_idx + self.rank, game_id_stride=self.world_size)
+        self.engine = Engine(ecfg, self.net, self.device)
+
+    def start(self, max_games=None, max_seconds=None, harvest_every=None):
+        """Runs until max_games finished / max_seconds elapsed (both None: forever, like the reference)."""
+        if self.engine is None:
+            self._make_engine()
+        pdc = self.config.play_data
+        t0 = time.time()
+        finished = 0
+        chunk = harvest_every or max(1, min(256, int(pdc.nb_game_in_file)))
+        while True:
+            target = finished + chunk
+            if max_games is not None:
+                target = min(target, max_games)
+            self.engine.run(finished_target=self.local_idx + (target - finished))
+            finished += self._harvest()
+            if max_games is not None and finished >= max_games:
+                break
+            if max_seconds is not None and time.time() - t0 >= max_seconds:
+                break
+        self._flush_files(force=True)
+        return finished
+
+    def _harvest(self):
+        n_total = 0
+        pdc, pc = self.config.play_data, self.config.play
+        while True:
+            games, ng, plies, _ = self.engine.poll_raw()
+            if ng == 0:
+                break
+            for i in range(ng):
+                g = games[i]
+                n_total += 1
+                self.local_idx += 1
+                self.game_idx += self.world_size
+                gp = [plies[j] for j in range(g.first_ply, g.first_ply + g.n_plies)]
+                self._finish_game(g)
+                # drop draw games with probability drop_draw_game_rate (self_play.py:182)
+                if g.black_z != 0 or pdc.drop_draw_game_rate <= np.random.random():
+                    self.buffer_games.append((_copy(g), [_copy(p) for p in gp]))
+                if pdc.enable_ggf_data:
+                    self.ggf_lines.append(self._ggf_of(g, gp))
+                if self.local_idx % pdc.nb_game_in_file == 0:
+                    self._flush_files()
+            with open(self.config.resource.self_play_game_idx_file, "wt") as f:
+                f.write(str(self.game_idx))
+            new_sims = self.decide_simulation_num_per_move(self.game_idx)
+            if new_sims and new_sims != pc.simulation_num_per_move:
+                try:
+                    self.engine.set_simulation_num(new_sims)
+                    pc.simulation_num_per_move = new_sims
+                except _cabi.RzError as ex:   # arenas were sized for fewer simulations: keep the current count
+                    logger.warning(str(ex))
+        return n_total
+
+    def _finish_game(self, g):
+        """worker/self_play.py:219-238 (resign false-positive statistics)"""
+        if g.winner == 1:
+            fp = bool(g.resigned_mask & 1)
+        elif g.winner == 2:
+            fp = bool(g.resigned_mask & 2)
+        else:
+            fp = bool(g.resigned_mask)
+        if not g.resign_enabled:
+            self.resign_test_game_count += 1
+            if fp:
+                self.false_positive_count_of_resign += 1
+            self.check_and_update_resignation_threshold()
+
+    def _ggf_of(self, g, gp):
+        """MoveHistory, worker/self_play.py:275-299"""
+        moves = []
+        for p in gp:
+            if p.action < 0:
+                continue
+            if (len(moves) % 2 == 0) == (p.player == 2):
+                moves.append(convert_action_to_move(None))
+            moves.append(f"{convert_action_to_move(int(p.action))}/{p.q * 10}/{p.n}")
+        return make_ggf_string("RAZ", "RAZ", moves=moves)
+
+    def _flush_files(self, force=False):
+        rc, pdc = self.config.resource, self.config.play_data
+        if self.buffer_games:
+            n_plies = sum(len(pl) for _, pl in self.buffer_games)
+            G = (_cabi.Game * len(self.buffer_games))()
+            P = (_cabi.Ply * max(1, n_plies))()
+            at = 0
+            for i, (g, pl) in enumerate(self.buffer_games):
+                G[i] = g
+                G[i].first_ply = at
+                for p in pl:
+                    P[at] = p
+                    at += 1
+            game_id = datetime.now().strftime("%Y%m%d-%H%M%S.%f")
+            if self.world_size > 1:
+                game_id += f"_r{self.rank}"
+            path = os.path.join(rc.play_data_dir, rc.play_data_filename_tmpl % game_id)
+            write_play_data(path, G, len(self.buffer_games), P, pdc.save_policy_of_tau_1, self.config.play.change_tau_turn)
+            logger.info(f"save play data to {path}")
+            self.files_written.append(path)
+            self.buffer_games = []
+            self.remove_play_data()
+        if self.ggf_lines and (force or len(self.ggf_lines) >= pdc.nb_game_in_ggf_file):
+            game_id = datetime.now().strftime("%Y%m%d-%H%M%S.%f")
+            path = os.path.join(rc.self_play_ggf_data_dir, rc.ggf_filename_tmpl % game_id)
+            with open(path, "wt") as f:
+                for line in self.ggf_lines:
+                    f.write(line + "\n")
+            self.ggf_lines = []
+
+    def remove_play_data(self):
+        """worker/self_play.py:209-217"""
+        rc = self.config.resource
+        from glob import glob
+        files = sorted(glob(os.path.join(rc.play_data_dir, rc.play_data_filename_tmpl % "*")))
+        if len(files) < self.config.play_data.max_file_num:
+            return
+        for i in range(len(files) - self.config.play_data.max_file_num):
+            try:
+                os.remove(files[i])
+            except OSError:
+                pass
+
+
+def _copy(struct):
+    c = type(struct)()
+    import ctypes
+    ctypes.memmove(ctypes.byref(c), ctypes.byref(struct), ctypes.sizeof(struct))
+    return c

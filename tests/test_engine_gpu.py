@@ -49,7 +49,7 @@ def replay_check(g):
         own, enemy = env.own_enemy()
         assert (ply["own"], ply["enemy"], ply["pid"]) == (own, enemy, env.next_player)
         legal = ob.find_correct_moves(own, enemy)
-        assert all((legal >> a) & 1 for a in np.nonzero(ply["N"])[0])
+        assert all((legal >> int(a)) & 1 for a in np.nonzero(ply["N"])[0])
         assert ply["action"] == -1 or (legal >> ply["action"]) & 1
         env.step(None if ply["action"] < 0 else ply["action"])
     assert env.done and env.winner == g["winner"] and (env.black, env.white) == (g["black"], g["white"])
