@@ -277,9 +277,9 @@ def main():
     cb = None
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        r, gps = cpu_baseline(n_search_plies=1, processes=cores)
+        r, gps = cpu_baseline(n_search_plies=3, processes=cores)
         cb = dict(value=gps, unit="games/s", cores=cores, kind="port",
-                  sample=f"{cores} processes x first searched ply (400 sims) of one game each; {r['expansions']} expansions in {r['wall_s']:.1f} s",
+                  sample=f"{cores} processes x first 3 searched plies (400 sims each) of one game each; {r['expansions']} expansions in {r['wall_s']:.1f} s; games/s = plies/s / 60",
                   expansions_per_sec=r["expansions_per_s"], mean_nn_batch=r["mean_batch"])
 
     line = dict(metric="self_play_games_per_sec", value=value, unit="games/s", n_gpus=world, steps=args.steps, warmup=args.warmup,

@@ -2,7 +2,6 @@
 i.e. ReversiPlayer / ReversiEnv semantics with a torch-fp32 CPU forward) timed on the host cores.
 Used ONLY by bench.py's cpu_baseline leg and `--impl reference` arm (the Python reference itself cannot
 travel to the GPU box and Keras/TensorFlow are not installable)."""
-import multiprocessing as mp
 import os
 import time
 
@@ -39,19 +38,33 @@ def _worker(args):
 
 def measure(model_kw, play_kw, n_search_plies=2, processes=None, torch_threads=1, seed=20260922, weight_seed=0):
     """Plays the first `n_search_plies` searched plies of one game per process, `processes` games in parallel
-    (the reference's multi_process_num workers, worker/self_play.py:36-41).  Returns aggregate rates."""
+    (the reference's multi_process_num workers, worker/self_play.py:36-41).  Workers are plain subprocesses
+    (no fork of a CUDA-initialised parent, no multiprocessing start-method pitfalls).  Returns aggregate rates."""
+    import json
+    import subprocess
+    import sys
     processes = processes or os.cpu_count() or 1
-    jobs = [(model_kw, weight_seed, play_kw, seed, i, n_search_plies, torch_threads) for i in range(processes)]
     t0 = time.perf_counter()
-    if processes == 1:
-        res = [_worker(jobs[0])]
-    else:
-        ctx = mp.get_context("spawn")
-        with ctx.Pool(processes) as pool:
-            res = pool.map(_worker, jobs)
+    env = dict(os.environ, OMP_NUM_THREADS=str(torch_threads), MKL_NUM_THREADS=str(torch_threads), CUDA_VISIBLE_DEVICES="")
+    procs = []
+    for i in range(processes):
+        job = json.dumps([model_kw, weight_seed, play_kw, seed, i, n_search_plies, torch_threads])
+        procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), job], stdout=subprocess.PIPE, text=True, env=env))
+    res = []
+    for pr in procs:
+        out, _ = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError("cpu baseline worker failed")
+        res.append(json.loads(out.strip().splitlines()[-1]))
     wall = max(r["seconds"] for r in res)
     plies = sum(r["searched_plies"] for r in res)
     exps = sum(r["expansions"] for r in res)
     return dict(wall_s=wall, total_wall_s=time.perf_counter() - t0, searched_plies=plies, expansions=exps,
                 plies_per_s=plies / wall, expansions_per_s=exps / wall, processes=processes, torch_threads=torch_threads,
                 mean_batch=exps / max(1, sum(r["nn_calls"] for r in res)))
+
+
+if __name__ == "__main__":
+    import json
+    import sys
+    print(json.dumps(_worker(tuple(json.loads(sys.argv[1])))))
