@@ -77,33 +77,48 @@ class ClockSampler:
         return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
 
 
-def cpu_baseline(n_search_plies, processes, torch_threads=1):
+def expansions_per_game():
+    """mean network evaluations per COMPLETE game of this workload, measured on the B200 engine by
+    `bench.py --full-games` (cold start, every game played from the first to the last ply) and committed under
+    profiles/; the fallback is the value probed on the reference (21 256 at sim = 400)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "full_games.json")) as f:
+            d = json.load(f)
+        return float(d["expansions_per_game"]), "measured: profiles/full_games.json (%d complete games)" % d["games"]
+    except Exception:
+        return 21256.0, "fallback: reference probe, SURVEY 3.1"
+
+
+def cpu_baseline(budget_s, processes=None, torch_threads=1):
     from oracle import selfplay_cpu
-    r = selfplay_cpu.measure({k: v for k, v in MODEL_KW.items()}, dict(PLAY_KW), n_search_plies=n_search_plies,
+    r = selfplay_cpu.measure({k: v for k, v in MODEL_KW.items()}, dict(PLAY_KW), budget_s=budget_s,
                              processes=processes, torch_threads=torch_threads)
-    games_per_s = r["plies_per_s"] / PLIES_PER_GAME
-    return r, games_per_s
+    epg, _ = expansions_per_game()
+    return r, r["expansions_per_s"] / epg
 
 
 def run_reference(args):
-    """CPU port of the reference's self-play worker, one game stream per host core (worker/self_play.py:36-41)."""
+    """CPU port of the reference's self-play worker, one game stream per usable host core
+    (worker/self_play.py:36-41); each step is a time-bounded sample of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    vals, last = [], None
+    from oracle import selfplay_cpu
+    cores = selfplay_cpu.usable_cores()
+    budget = 12.0
+    vals = []
     for i in range(args.warmup + args.steps):
-        r, gps = cpu_baseline(n_search_plies=1, processes=cores)
-        last = r
+        r, gps = cpu_baseline(budget_s=budget, processes=cores)
         if i >= args.warmup:
             vals.append((gps, r))
     gps = sum(v for v, _ in vals) / len(vals)
     eps = sum(r["expansions_per_s"] for _, r in vals) / len(vals)
-    ms = 1e3 * sum(r["wall_s"] for _, r in vals) / len(vals)
-    sample = f"each step: {cores} processes x first searched ply (400 simulations) of one game, torch fp32 CPU forward, 1 thread/process"
+    epg, epg_src = expansions_per_game()
+    sample = (f"each step: {cores} processes x {budget:.0f} s of one game each from the opening (400 sims/move), torch fp32 CPU forward, "
+              f"1 thread/process; games/s = expansions/s / {epg:.0f} expansions per complete game ({epg_src})")
     line = dict(impl="reference", metric="self_play_games_per_sec", value=gps, unit="games/s", n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                data="synthetic", config=workload_config(args, cores=cores), expansions_per_sec=eps,
+                warmup=args.warmup, ms_per_step=budget * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", config=workload_config(args, cores=cores), node_expansions_per_sec=eps,
                 cpu_baseline=dict(value=gps, unit="games/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=gps, unit="games/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
@@ -127,10 +142,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--games", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-games", type=int, default=0, metavar="G",
+                    help="calibration: play G complete games from a cold start and write gpurun_out/full_games.json")
     args = ap.parse_args()
     if args.impl == "reference":
-        if args.steps > 8:
-            args.steps, args.warmup = 2, 1  # each step is ~10-20 s of CPU work
+        if args.steps > 4:
+            args.steps, args.warmup = 2, 0  # each step is a 12 s time-bounded CPU sample (+ process start-up)
         return run_reference(args)
     if args.warmup < 3:
         args.warmup = 3
@@ -175,6 +192,25 @@ def main():
                                             game_id_stride=world, warm_start=True)
         return E.Engine(cfg, net, local)
 
+    if args.full_games:
+        cfg = E.engine_cfg_from_play_config(pp, games=args.full_games, seed=20260922, eval_mode=E.EVAL_NET, max_games=args.full_games)
+        eng = E.Engine(cfg, net, local)
+        t0 = time.perf_counter()
+        eng.run(finished_target=args.full_games)
+        dt = time.perf_counter() - t0
+        gs = eng.poll()
+        st = eng.stats()
+        out = dict(games=len(gs), expansions_per_game=sum(g["expansions"] for g in gs) / len(gs),
+                   simulations_per_game=sum(g["simulations"] for g in gs) / len(gs), plies_per_game=sum(len(g["plies"]) for g in gs) / len(gs),
+                   black_wins=sum(g["winner"] == 1 for g in gs), white_wins=sum(g["winner"] == 2 for g in gs), draws=sum(g["winner"] == 3 for g in gs),
+                   seconds=dt, games_per_sec_cold_start=len(gs) / dt, waves=st["waves"], max_nodes_used=st["max_nodes_used"],
+                   max_edges_used=st["max_edges_used"], workload=workload_config(args)["workload"])
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "full_games.json"), "w") as f:
+            json.dump(out, f)
+        print(json.dumps(out), flush=True)
+        return
+
     # ---- device-resident measurement: `value` -------------------------------------------------------------
     eng = make_engine()
     eng.run(max_waves=args.warmup)
@@ -192,8 +228,7 @@ def main():
     s1 = eng.stats()
     d = {k: s1[k] - s0[k] for k in s1}
     run_ms = d["run_ms"]
-    finished_games = eng.poll()
-    plies_per_game = (sum(len(g["plies"]) for g in finished_games) / len(finished_games)) if finished_games else PLIES_PER_GAME
+    eng.poll()
     eng.close()
     counts = torch.tensor([d["games_finished"], d["expansions"], d["simulations"], d["plies"], d["nn_launches"] + d["mcts_launches"]],
                           dtype=torch.float64, device=f"cuda:{local}")
@@ -204,8 +239,13 @@ def main():
     games, exps, sims, plies, launches = [float(x) for x in counts.tolist()]
     run_ms, nn_ms, mcts_ms = [float(x) for x in tmax.tolist()]
     secs = run_ms / 1e3
-    value = games / secs
     exp_per_s = exps / secs
+    epg, epg_src = expansions_per_game()
+    # steady-state rate of complete games: the network evaluations are ~all of the cost, the leaf batches stay full
+    # whatever the mix of game phases, so games/s = expansions/s / (expansions per complete game).  The raw count of
+    # games that happened to finish inside the window is reported next to it (it over-counts: endgame plies are cheap,
+    # so warm-started slots near the end of their game finish in a burst).
+    value = exp_per_s / epg
 
     # ---- end to end through the public worker path: host weights -> device, waves, harvest, play_data files ----
     import tempfile
@@ -239,19 +279,21 @@ def main():
     worker._flush_files(force=True)
     torch.cuda.synchronize()
     e2e_secs = time.perf_counter() - t0
+    e2e_exps = float(worker.engine.stats()["expansions"])
     file_bytes = sum(os.path.getsize(p) for p in worker.files_written)
     d2h = n_e2e * (48 + 60 * 288) + (args.steps // 8 + 1) * (80 + 2 * args.games)
-    e2e_t = torch.tensor([float(n_e2e), e2e_secs], dtype=torch.float64, device=f"cuda:{local}")
+    e2e_t = torch.tensor([float(n_e2e), e2e_secs, e2e_exps], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         g_ = e2e_t.clone(); dist.all_reduce(g_, op=dist.ReduceOp.SUM)
         m_ = e2e_t.clone(); dist.all_reduce(m_, op=dist.ReduceOp.MAX)
-        n_e2e_all, e2e_secs = float(g_[0]), float(m_[1])
+        n_e2e_all, e2e_secs, e2e_exps = float(g_[0]), float(m_[1]), float(g_[2])
     else:
         n_e2e_all = float(n_e2e)
+    e2e_value = e2e_exps / e2e_secs / expansions_per_game()[0]
     worker.engine.close()
     import shutil
     shutil.rmtree(tmp, ignore_errors=True)
-    e2e_value = n_e2e_all / e2e_secs
+    st_e2e = None
 
     if rank != 0:
         if world > 1:
@@ -276,22 +318,23 @@ def main():
 
     cb = None
     if not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        r, gps = cpu_baseline(n_search_plies=3, processes=cores)
-        cb = dict(value=gps, unit="games/s", cores=cores, kind="port",
-                  sample=f"{cores} processes x first 3 searched plies (400 sims each) of one game each; {r['expansions']} expansions in {r['wall_s']:.1f} s; games/s = plies/s / 60",
+        r, gps = cpu_baseline(budget_s=15.0)
+        cb = dict(value=gps, unit="games/s", cores=r["processes"], kind="port",
+                  sample=f"{r['processes']} processes x 15 s of one game each from the opening (400 sims/move); {r['expansions']} expansions; "
+                         f"games/s = expansions/s / {epg:.0f}",
                   expansions_per_sec=r["expansions_per_s"], mean_nn_batch=r["mean_batch"])
 
     line = dict(metric="self_play_games_per_sec", value=value, unit="games/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=run_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16 operands / f32 accumulate",
                 data="synthetic (random-init ch5 weights, self-generated games)",
-                config=workload_config(args, games_finished_in_window=games, plies_decided=plies,
-                                       games_per_sec_plies_based=plies / secs / plies_per_game, plies_per_game_observed=plies_per_game,
-                                       timing="CUDA events on the engine stream, first to last wave; max over ranks"),
+                config=workload_config(args, games_finished_in_window=games, games_per_sec_finished_in_window=games / secs,
+                                       plies_decided=plies, expansions_per_game=epg, expansions_per_game_source=epg_src,
+                                       value_definition="node_expansions_per_sec / expansions_per_game",
+                                       timing="CUDA events on the engine streams, first to last wave; max over ranks"),
                 node_expansions_per_sec=exp_per_s, simulations_per_sec=sims / secs,
                 roofline=roofline, cpu_baseline=cb, clocks=clocks,
                 e2e=dict(value=e2e_value, unit="games/s", h2d_bytes_per_step=int(n_blob * 4 / args.steps), d2h_bytes_per_step=int(d2h / args.steps),
-                         play_data_bytes_written=file_bytes, games=n_e2e_all, seconds=e2e_secs,
+                         play_data_bytes_written=file_bytes, games_harvested=n_e2e_all, expansions=e2e_exps, seconds=e2e_secs,
                          what="host weight blob -> device + pack, engine create, K waves, harvest, play_*.json written"),
                 gpu_launches=int(launches))
     print(json.dumps(line), flush=True)

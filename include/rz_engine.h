@@ -152,7 +152,11 @@ typedef struct rz_engine_cfg {
                                        random legal plies, so a fresh engine is in steady state (game phases
                                        spread uniformly) instead of all slots marching in lock step; those
                                        pre-played plies are not searched and not recorded */
-    int32_t reserved;
+    int32_t overlap_groups;         /* 0 = auto (2 when games >= 256), 1, or 2: slot groups whose MCTS tick overlaps
+                                       the other group's network launch on a second stream */
+    int32_t max_searches_per_game;  /* sizes the per-game node arena: nodes = this x simulation_num_per_move;
+                                       0 = 60 x min(thinking_loop, 2).  Rethinking (thinking_loop > 1) is skipped
+                                       when the arena could no longer hold one search per remaining ply. */
     float c_puct;                   /* :135 */
     float noise_eps;                /* :136 */
     float dirichlet_alpha;          /* :137 */

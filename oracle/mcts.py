@@ -20,6 +20,8 @@ Differences from the reference, all deliberate and documented in DESIGN.md:
     promotion on the reference's expressions (float32 priors, float64 Q/U).
   * RNG: Philox4x32-10 streams (oracle/philox.py) instead of numpy MT19937.
 """
+import time
+
 import numpy as np
 
 from . import bitboard as bb
@@ -122,8 +124,13 @@ class Descent:
         self.path = []  # (node, action, mover_is_root)
 
 
+class TimeUp(Exception):
+    """raised inside a search when SelfPlayGame.deadline (time.perf_counter value) has passed"""
+
+
 class SelfPlayGame:
     """One self-play game: both players, shared (or separate) statistics, compact per-ply log."""
+    deadline = None  # optional wall-clock bound used by the CPU-baseline timing (oracle/selfplay_cpu.py)
 
     def __init__(self, pp, api, seed=0, game_id=0, noise_rng=None):
         self.pp, self.api, self.seed, self.game_id = pp, api, seed, game_id
@@ -216,6 +223,9 @@ class SelfPlayGame:
                 continue
             self.n_waves += 1
             self._evaluate(pending, pid)
+            if self.deadline is not None and time.perf_counter() > self.deadline:
+                self.n_sims += started
+                raise TimeUp()
         self.n_sims += started
 
     def _evaluate(self, pending, pid):

@@ -8,8 +8,20 @@ import time
 import numpy as np
 
 
+def usable_cores():
+    """cores this process may actually use: affinity mask, capped by the cgroup CPU quota if any"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return n
+
+
 def _worker(args):
-    (model_kw, weight_seed, play_kw, seed, game_id, n_search_plies, torch_threads) = args
+    (model_kw, weight_seed, play_kw, seed, game_id, budget_s, torch_threads) = args
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
@@ -22,33 +34,35 @@ def _worker(args):
     api = onn.OracleNetAPI(M.build_random_weights(mc, weight_seed), mc.res_layer_num)
     pp = mcts.PlayParams(**play_kw)
     game = mcts.SelfPlayGame(pp, api, seed=seed, game_id=game_id)
+    api.predict(np.zeros((8, 2, 8, 8), np.uint8))  # warm-up (thread pools, first-touch)
+    api.rows = api.calls = 0
     t0 = time.perf_counter()
-    searched = 0
+    game.deadline = t0 + budget_s
     e = game.env
-    while not e.done and searched < n_search_plies:
-        own, enemy = e.own_enemy()
-        turn = e.turn
-        a = game.decide(own, enemy, e.next_player)
-        if turn > 0:
-            searched += 1
-        e.step(a)
+    try:
+        while not e.done:
+            own, enemy = e.own_enemy()
+            a = game.decide(own, enemy, e.next_player)
+            e.step(a)
+    except mcts.TimeUp:
+        pass
     dt = time.perf_counter() - t0
-    return dict(seconds=dt, searched_plies=searched, expansions=api.rows, nn_calls=api.calls, sims=game.n_sims)
+    return dict(seconds=dt, plies=len(game.plies), expansions=api.rows, nn_calls=api.calls, sims=game.n_sims)
 
 
-def measure(model_kw, play_kw, n_search_plies=2, processes=None, torch_threads=1, seed=20260922, weight_seed=0):
-    """Plays the first `n_search_plies` searched plies of one game per process, `processes` games in parallel
-    (the reference's multi_process_num workers, worker/self_play.py:36-41).  Workers are plain subprocesses
-    (no fork of a CUDA-initialised parent, no multiprocessing start-method pitfalls).  Returns aggregate rates."""
+def measure(model_kw, play_kw, budget_s=15.0, processes=None, torch_threads=1, seed=20260922, weight_seed=0):
+    """`processes` game streams in parallel (the reference's multi_process_num workers,
+    worker/self_play.py:36-41), each playing one game from the start for `budget_s` seconds of wall clock.
+    Workers are plain subprocesses (no fork of a CUDA-initialised parent).  Returns aggregate rates."""
     import json
     import subprocess
     import sys
-    processes = processes or os.cpu_count() or 1
+    processes = processes or usable_cores()
     t0 = time.perf_counter()
     env = dict(os.environ, OMP_NUM_THREADS=str(torch_threads), MKL_NUM_THREADS=str(torch_threads), CUDA_VISIBLE_DEVICES="")
     procs = []
     for i in range(processes):
-        job = json.dumps([model_kw, weight_seed, play_kw, seed, i, n_search_plies, torch_threads])
+        job = json.dumps([model_kw, weight_seed, play_kw, seed, i, budget_s, torch_threads])
         procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), job], stdout=subprocess.PIPE, text=True, env=env))
     res = []
     for pr in procs:
@@ -56,11 +70,11 @@ def measure(model_kw, play_kw, n_search_plies=2, processes=None, torch_threads=1
         if pr.returncode != 0:
             raise RuntimeError("cpu baseline worker failed")
         res.append(json.loads(out.strip().splitlines()[-1]))
-    wall = max(r["seconds"] for r in res)
-    plies = sum(r["searched_plies"] for r in res)
     exps = sum(r["expansions"] for r in res)
-    return dict(wall_s=wall, total_wall_s=time.perf_counter() - t0, searched_plies=plies, expansions=exps,
-                plies_per_s=plies / wall, expansions_per_s=exps / wall, processes=processes, torch_threads=torch_threads,
+    sims = sum(r["sims"] for r in res)
+    return dict(budget_s=budget_s, total_wall_s=time.perf_counter() - t0, expansions=exps, simulations=sims,
+                expansions_per_s=sum(r["expansions"] / r["seconds"] for r in res),
+                simulations_per_s=sum(r["sims"] / r["seconds"] for r in res), processes=processes, torch_threads=torch_threads,
                 mean_batch=exps / max(1, sum(r["nn_calls"] for r in res)))
 
 

@@ -496,7 +496,9 @@ struct Ctx {
         const double value_diff = q_choice - q_abv;
         sl.tl++;
         const bool accept = turn <= c.start_rethinking_turn || (value_diff > -0.01 && ed[choice].n >= c.required_visit);
-        if (!accept && sl.tl < c.thinking_loop && turn > 0) {  // think again: another simulation_num_per_move
+        // (rethinking is skipped when the node arena could not also hold one search for every remaining ply)
+        const bool room = (u64)sl.n_nodes + (u64)c.S * (u64)(61 - turn) + 64 <= (u64)c.nodes_cap;
+        if (!accept && sl.tl < c.thinking_loop && turn > 0 && room) {  // think again: another simulation_num_per_move
             begin_search(own, enemy, pid);
             return;
         }
@@ -529,11 +531,12 @@ struct Ctx {
 // ---- the per-wave kernel: one thread per game slot ------------------------------------------------------
 constexpr int kTickThreads = 64;
 
-__global__ void __launch_bounds__(kTickThreads) tick_kernel(const DevCfg c, const DevPtrs p) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(kTickThreads) tick_kernel(const DevCfg c, const DevPtrs p, const int slot0, const int slot_end,
+                                                            const int group) {
+    const int s = slot0 + blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int n_leaves = 0;
-    if (s < c.G) {
+    if (s < slot_end) {
         Ctx x(c, p, s);
         Slot& sl = x.sl;
         if (p.status->error == 0 && sl.phase != PH_IDLE) {
@@ -575,12 +578,13 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const DevCfg c, cons
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     uint32_t base = 0;
-    if (lane == 31 && total > 0) base = atomicAdd(p.batch_count, (uint32_t)total);
+    if (lane == 31 && total > 0) base = atomicAdd(p.batch_count + group * 64, (uint32_t)total);
     base = __shfl_sync(0xffffffffu, base, 31);
     if (n_leaves > 0) {
         Slot& sl = p.slots[s];
         Descent* desc = p.desc + (size_t)s * c.K;
-        uint32_t at = base + (uint32_t)(incl - n_leaves);
+        // each group owns the batch rows [slot0 * K, slot_end * K); leaf_index is the absolute row
+        uint32_t at = (uint32_t)slot0 * (uint32_t)c.K + base + (uint32_t)(incl - n_leaves);
         for (int j = 0; j < n_leaves; ++j, ++at) {
             Descent& d = desc[sl.pending[j]];
             d.leaf_index = at;
@@ -654,7 +658,10 @@ struct rz_engine {
     DevPtrs dp;
     rz_net* net;
     int device;
-    cudaStream_t stream;
+    cudaStream_t stream;      // group 0 + all host<->device traffic
+    cudaStream_t stream2;     // group 1 (tick of one group overlaps the network launch of the other)
+    int n_groups;
+    int group_slot0[3];
     void* arena[16];
     int n_arena;
     Status* h_status;     // pinned
@@ -663,19 +670,21 @@ struct rz_engine {
     uint64_t finished_total;
     std::deque<FinishedGame> queue;
     // device timing: 3 events per queued wave (before tick, between tick and evaluation, after evaluation)
-    cudaEvent_t ev[3 * 8];
-    cudaEvent_t ev_run[2];
+    cudaEvent_t ev[2 * 3 * 8];  // [group][wave in burst][3]
+    cudaEvent_t ev_run[3];     // run start, run end, group-1 join
     int ev_used;
     double nn_ms, mcts_ms, run_ms;
 };
 
 static int collect_timing(rz_engine* e) {  // call after the stream has been synchronised
-    for (int i = 0; i < e->ev_used; ++i) {
-        float a = 0.f, b = 0.f;
-        RZ_CUDA_TRY(cudaEventElapsedTime(&a, e->ev[3 * i], e->ev[3 * i + 1]));
-        RZ_CUDA_TRY(cudaEventElapsedTime(&b, e->ev[3 * i + 1], e->ev[3 * i + 2]));
-        e->mcts_ms += a; e->nn_ms += b;
-    }
+    for (int g = 0; g < e->n_groups; ++g)
+        for (int i = 0; i < e->ev_used; ++i) {
+            float a = 0.f, b = 0.f;
+            cudaEvent_t* ev = e->ev + (g * 8 + i) * 3;
+            RZ_CUDA_TRY(cudaEventElapsedTime(&a, ev[0], ev[1]));
+            RZ_CUDA_TRY(cudaEventElapsedTime(&b, ev[1], ev[2]));
+            e->mcts_ms += a; e->nn_ms += b;
+        }
     e->ev_used = 0;
     return RZ_OK;
 }
@@ -717,27 +726,43 @@ static int drain_mailboxes(rz_engine* e) {
 static int launch_wave(rz_engine* e) {
     const DevCfg& c = e->dc;
     const bool timed = e->ev_used < 8;
-    if (timed) RZ_CUDA_TRY(cudaEventRecord(e->ev[3 * e->ev_used], e->stream));
-    RZ_CUDA_TRY(cudaMemsetAsync(e->dp.batch_count, 0, sizeof(uint32_t), e->stream));
-    tick_kernel<<<(c.G + kTickThreads - 1) / kTickThreads, kTickThreads, 0, e->stream>>>(c, e->dp);
-    RZ_LAUNCH_CHECK();
-    e->mcts_launches++;
-    if (timed) RZ_CUDA_TRY(cudaEventRecord(e->ev[3 * e->ev_used + 1], e->stream));
-    if (e->cfg.eval_mode == RZ_EVAL_FAKE) {
-        fake_eval_kernel<<<num_sms() * 4, 256, 0, e->stream>>>(e->dp.batch_own, e->dp.batch_enemy, e->dp.batch_count, e->dp.policy, e->dp.value);
+    for (int g = 0; g < e->n_groups; ++g) {
+        cudaStream_t st = g == 0 ? e->stream : e->stream2;
+        const int s0 = e->group_slot0[g], s1 = e->group_slot0[g + 1];
+        cudaEvent_t* ev = e->ev + (g * 8 + e->ev_used) * 3;
+        uint32_t* count = e->dp.batch_count + g * 64;
+        const size_t row0 = (size_t)s0 * c.K, rows = (size_t)(s1 - s0) * c.K;
+        if (timed) RZ_CUDA_TRY(cudaEventRecord(ev[0], st));
+        RZ_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(uint32_t), st));
+        tick_kernel<<<(s1 - s0 + kTickThreads - 1) / kTickThreads, kTickThreads, 0, st>>>(c, e->dp, s0, s1, g);
         RZ_LAUNCH_CHECK();
         e->mcts_launches++;
-    } else {
-        RZ_TRY(net_forward_counted(e->net, e->dp.batch_own, e->dp.batch_enemy, e->dp.policy, e->dp.value, e->dp.batch_count,
-                                   (size_t)c.G * c.K, e->cfg.net_impl, e->stream));
-        e->nn_launches++;
+        if (timed) RZ_CUDA_TRY(cudaEventRecord(ev[1], st));
+        if (e->cfg.eval_mode == RZ_EVAL_FAKE) {
+            fake_eval_kernel<<<num_sms() * 4, 256, 0, st>>>(e->dp.batch_own + row0, e->dp.batch_enemy + row0, count, e->dp.policy + row0 * 64,
+                                                          e->dp.value + row0);
+            RZ_LAUNCH_CHECK();
+            e->mcts_launches++;
+        } else {
+            RZ_TRY(net_forward_counted(e->net, e->dp.batch_own + row0, e->dp.batch_enemy + row0, e->dp.policy + row0 * 64, e->dp.value + row0,
+                                       count, rows, e->cfg.net_impl, st));
+            e->nn_launches++;
+        }
+        if (timed) RZ_CUDA_TRY(cudaEventRecord(ev[2], st));
     }
-    if (timed) { RZ_CUDA_TRY(cudaEventRecord(e->ev[3 * e->ev_used + 2], e->stream)); e->ev_used++; }
+    if (timed) e->ev_used++;
     e->waves++;
     return RZ_OK;
 }
 
+static int sync_all(rz_engine* e) {
+    if (e->n_groups > 1) RZ_CUDA_TRY(cudaStreamSynchronize(e->stream2));
+    RZ_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return RZ_OK;
+}
+
 static int read_status(rz_engine* e) {
+    RZ_TRY(sync_all(e));
     RZ_CUDA_TRY(cudaMemcpyAsync(e->h_status, e->dp.status, sizeof(Status), cudaMemcpyDeviceToHost, e->stream));
     RZ_CUDA_TRY(cudaStreamSynchronize(e->stream));
     RZ_TRY(collect_timing(e));
@@ -764,10 +789,16 @@ int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net, int device, rz_engin
     if (!e) { set_error("out of host memory"); return RZ_ENOMEM; }
     e->cfg = *cfg; e->net = net; e->device = device; e->n_arena = 0;
     e->waves = e->nn_launches = e->mcts_launches = e->finished_total = 0;
-    e->h_status = nullptr; e->h_flags = nullptr; e->stream = nullptr;
+    e->h_status = nullptr; e->h_flags = nullptr; e->stream = nullptr; e->stream2 = nullptr;
     e->ev_used = 0; e->nn_ms = e->mcts_ms = e->run_ms = 0.0;
-    for (int i = 0; i < 24; ++i) e->ev[i] = nullptr;
-    e->ev_run[0] = e->ev_run[1] = nullptr;
+    for (int i = 0; i < 48; ++i) e->ev[i] = nullptr;
+    e->ev_run[0] = e->ev_run[1] = e->ev_run[2] = nullptr;
+    // two slot groups on two streams: the MCTS tick of one group runs underneath the network launch of the other
+    e->n_groups = cfg->overlap_groups == 1 ? 1 : (cfg->overlap_groups == 2 ? 2 : (cfg->games >= 256 ? 2 : 1));
+    if (cfg->games < 2) e->n_groups = 1;
+    e->group_slot0[0] = 0;
+    e->group_slot0[1] = e->n_groups == 2 ? (cfg->games + 1) / 2 : cfg->games;
+    e->group_slot0[2] = cfg->games;
     DevCfg& c = e->dc;
     c.G = cfg->games; c.S = cfg->simulation_num_per_move; c.K = cfg->parallel_search_num; c.vl = cfg->virtual_loss;
     c.change_tau_turn = cfg->change_tau_turn; c.thinking_loop = cfg->thinking_loop; c.required_visit = cfg->required_visit_to_decide_action;
@@ -778,7 +809,9 @@ int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net, int device, rz_engin
     c.disable_resignation_rate = cfg->disable_resignation_rate;
     c.seed = cfg->seed; c.first_game_id = cfg->first_game_id; c.game_id_stride = cfg->game_id_stride; c.max_games = cfg->max_games;
     // every simulation creates at most one node; a game has at most 60 searched plies
-    uint64_t nodes = (uint64_t)60 * c.S * (c.thinking_loop > 2 ? 2 : c.thinking_loop) + 64;
+    const uint64_t searches = cfg->max_searches_per_game > 0 ? (uint64_t)cfg->max_searches_per_game
+                                                              : (uint64_t)60 * (c.thinking_loop > 2 ? 2 : c.thinking_loop);
+    uint64_t nodes = searches * c.S + 64;
     if (nodes > 0xFFFF0) nodes = 0xFFFF0;
     c.nodes_cap = (uint32_t)nodes;
     c.edges_cap = c.nodes_cap * 14;
@@ -787,6 +820,7 @@ int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net, int device, rz_engin
     c.hash_cap = h;
     int rc = RZ_OK;
     cudaError_t ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking);
     if (ce != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(ce)); delete e; return RZ_ECUDA; }
     const size_t G = c.G, B = G * c.K;
     DevPtrs& p = e->dp;
@@ -799,16 +833,16 @@ int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net, int device, rz_engin
     if (!rc) rc = dev_alloc(e, (void**)&p.mail_hdr, G * 2 * sizeof(rz_game), true);
     if (!rc) rc = dev_alloc(e, (void**)&p.mail_flag, G * 2, true);
     if (!rc) rc = dev_alloc(e, (void**)&p.status, sizeof(Status), true);
-    if (!rc) rc = dev_alloc(e, (void**)&p.batch_count, 256, true);
+    if (!rc) rc = dev_alloc(e, (void**)&p.batch_count, 1024, true);
     if (!rc) rc = dev_alloc(e, (void**)&p.batch_own, (B + 2) * sizeof(u64), true);
     if (!rc) rc = dev_alloc(e, (void**)&p.batch_enemy, (B + 2) * sizeof(u64), true);
     if (!rc) rc = dev_alloc(e, (void**)&p.policy, (B + 2) * 64 * sizeof(float), true);
     if (!rc) rc = dev_alloc(e, (void**)&p.value, (B + 2) * sizeof(float), true);
     if (!rc && cudaMallocHost((void**)&e->h_status, sizeof(Status)) != cudaSuccess) { set_error("cudaMallocHost failed"); rc = RZ_ENOMEM; }
     if (!rc && cudaMallocHost((void**)&e->h_flags, G * 2) != cudaSuccess) { set_error("cudaMallocHost failed"); rc = RZ_ENOMEM; }
-    for (int i = 0; i < 24 && !rc; ++i)
+    for (int i = 0; i < 48 && !rc; ++i)
         if (cudaEventCreate(&e->ev[i]) != cudaSuccess) { set_error("cudaEventCreate failed"); rc = RZ_ECUDA; }
-    for (int i = 0; i < 2 && !rc; ++i)
+    for (int i = 0; i < 3 && !rc; ++i)
         if (cudaEventCreate(&e->ev_run[i]) != cudaSuccess) { set_error("cudaEventCreate failed"); rc = RZ_ECUDA; }
     if (rc) { rz_engine_destroy(e); return rc; }
     init_slots_kernel<<<(c.G + 127) / 128, 128, 0, e->stream>>>(c, p);
@@ -821,13 +855,15 @@ int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net, int device, rz_engin
 int rz_engine_destroy(rz_engine* e) {
     if (!e) return RZ_OK;
     cudaSetDevice(e->device);
+    if (e->stream2) cudaStreamSynchronize(e->stream2);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (int i = 0; i < e->n_arena; ++i) cudaFree(e->arena[i]);
     if (e->h_status) cudaFreeHost(e->h_status);
     if (e->h_flags) cudaFreeHost(e->h_flags);
-    for (int i = 0; i < 24; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
-    for (int i = 0; i < 2; ++i) if (e->ev_run[i]) cudaEventDestroy(e->ev_run[i]);
+    for (int i = 0; i < 48; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    for (int i = 0; i < 3; ++i) if (e->ev_run[i]) cudaEventDestroy(e->ev_run[i]);
     if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->stream2) cudaStreamDestroy(e->stream2);
     cudaGetLastError();
     delete e;
     return RZ_OK;
@@ -838,7 +874,9 @@ int rz_engine_run(rz_engine* e, uint64_t finished_target, uint64_t max_waves) {
     RZ_CUDA_TRY(cudaSetDevice(e->device));
     const uint64_t wave0 = e->waves;
     const int kCheck = 8;  // waves queued between host checks
+    RZ_TRY(sync_all(e));
     RZ_CUDA_TRY(cudaEventRecord(e->ev_run[0], e->stream));
+    if (e->n_groups > 1) RZ_CUDA_TRY(cudaStreamWaitEvent(e->stream2, e->ev_run[0], 0));
     int rc_loop = RZ_OK;
     while (true) {
         if (e->finished_total >= finished_target && finished_target > 0) break;
@@ -854,8 +892,12 @@ int rz_engine_run(rz_engine* e, uint64_t finished_target, uint64_t max_waves) {
         }
     }
     (void)rc_loop;
+    if (e->n_groups > 1) {
+        RZ_CUDA_TRY(cudaEventRecord(e->ev_run[2], e->stream2));
+        RZ_CUDA_TRY(cudaStreamWaitEvent(e->stream, e->ev_run[2], 0));
+    }
     RZ_CUDA_TRY(cudaEventRecord(e->ev_run[1], e->stream));
-    RZ_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    RZ_TRY(sync_all(e));
     float ms = 0.f;
     RZ_CUDA_TRY(cudaEventElapsedTime(&ms, e->ev_run[0], e->ev_run[1]));
     e->run_ms += ms;
@@ -882,6 +924,7 @@ int rz_engine_poll(rz_engine* e, rz_game* games, size_t game_cap, size_t* n_game
 int rz_engine_stats(rz_engine* e, rz_stats* out) {
     RZ_REQUIRE(e && out, "rz_engine_stats: null pointer");
     RZ_CUDA_TRY(cudaSetDevice(e->device));
+    RZ_TRY(sync_all(e));
     RZ_CUDA_TRY(cudaMemcpyAsync(e->h_status, e->dp.status, sizeof(Status), cudaMemcpyDeviceToHost, e->stream));
     RZ_CUDA_TRY(cudaStreamSynchronize(e->stream));
     const Status& s = *e->h_status;
@@ -895,7 +938,9 @@ int rz_engine_stats(rz_engine* e, rz_stats* out) {
 
 int rz_engine_set_simulation_num(rz_engine* e, int32_t sims) {
     RZ_REQUIRE(e && sims >= 1, "rz_engine_set_simulation_num: bad argument");
-    uint64_t need = (uint64_t)60 * sims * (e->dc.thinking_loop > 2 ? 2 : e->dc.thinking_loop) + 64;
+    const uint64_t searches = e->cfg.max_searches_per_game > 0 ? (uint64_t)e->cfg.max_searches_per_game
+                                                                  : (uint64_t)60 * (e->dc.thinking_loop > 2 ? 2 : e->dc.thinking_loop);
+    uint64_t need = searches * sims + 64;
     RZ_REQUIRE(need <= e->dc.nodes_cap, "simulation count %d exceeds the arenas sized at creation", sims);
     e->dc.S = sims;
     e->cfg.simulation_num_per_move = sims;
@@ -915,9 +960,11 @@ int rz_engine_search_root(rz_engine* e, uint64_t own, uint64_t enemy, int player
                           float* w_sum) {
     RZ_REQUIRE(e && n_visit && w_sum && (player == 1 || player == 2) && slot >= 0 && slot < e->dc.G, "rz_engine_search_root: bad argument");
     RZ_CUDA_TRY(cudaSetDevice(e->device));
+    RZ_TRY(sync_all(e));
     RZ_CUDA_TRY(cudaMemsetAsync(e->dp.status, 0, sizeof(Status), e->stream));
     setup_search_root_kernel<<<(e->dc.G + 127) / 128, 128, 0, e->stream>>>(e->dc, e->dp, own, enemy, player, keep_tree);
     RZ_LAUNCH_CHECK();
+    RZ_CUDA_TRY(cudaStreamSynchronize(e->stream));
     for (int it = 0; it < 1000000; ++it) {
         for (int i = 0; i < 8; ++i) RZ_TRY(launch_wave(e));
         RZ_TRY(read_status(e));

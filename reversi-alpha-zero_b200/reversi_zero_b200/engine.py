@@ -10,7 +10,8 @@ EVAL_NET, EVAL_FAKE = 0, 1
 
 
 def engine_cfg_from_play_config(pc, pdc=None, games=1024, seed=0, eval_mode=EVAL_NET, net_impl=0, first_game_id=0,
-                                game_id_stride=1, max_games=0, warm_start=False):
+                                game_id_stride=1, max_games=0, warm_start=False, overlap_groups=0,
+                                max_searches_per_game=0):
     """Build an rz_engine_cfg from objects with the reference's PlayConfig / PlayDataConfig fields
     (config.py:116-166)."""
     cfg = _cabi.EngineCfg()
@@ -29,6 +30,8 @@ def engine_cfg_from_play_config(pc, pdc=None, games=1024, seed=0, eval_mode=EVAL
     cfg.net_impl = net_impl
     cfg.max_plies = 64
     cfg.warm_start = 1 if warm_start else 0
+    cfg.overlap_groups = overlap_groups
+    cfg.max_searches_per_game = max_searches_per_game
     cfg.c_puct = float(pc.c_puct)
     cfg.noise_eps = float(pc.noise_eps)
     cfg.dirichlet_alpha = float(pc.dirichlet_alpha)

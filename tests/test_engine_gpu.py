@@ -23,6 +23,7 @@ def params(**kw):
 
 
 def make_engine(pp, games, seed, **kw):
+    kw.setdefault("max_searches_per_game", 60 * pp.thinking_loop)  # arena large enough that rethinking is never skipped
     cfg = E.engine_cfg_from_play_config(pp, games=games, seed=seed, eval_mode=E.EVAL_FAKE, **kw)
     return E.Engine(cfg)
 
@@ -64,7 +65,7 @@ def replay_check(g):
 def test_full_games_exact(kw, tmp_path):
     pp = params(**kw)
     n_games = 6
-    eng = make_engine(pp, games=4, seed=21, max_games=n_games)  # 4 slots, 6 games: slots 0,1 play two games each
+    eng = make_engine(pp, games=4, seed=21, max_games=n_games, overlap_groups=2)  # 4 slots (2 groups), 6 games: slots 0,1 play two games each
     eng.run(finished_target=n_games)
     raw_games, ng, raw_plies, _ = eng.poll_raw()
     assert ng == n_games
