@@ -22,6 +22,7 @@
 #include <deque>
 #include <new>
 #include <vector>
+#include <stdlib.h>
 #include <string.h>
 #include "rz_bitboard.cuh"
 #include "rz_net.cuh"
@@ -594,6 +595,8 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const DevCfg c, cons
     }
 }
 
+#include "rz_engine_warp.cuh"
+
 // RZ_EVAL_FAKE: policy 1/64, value (#own - #enemy)/64 (oracle/nn.py FakeNetAPI)
 __global__ void fake_eval_kernel(const u64* __restrict__ own, const u64* __restrict__ enemy, const uint32_t* __restrict__ count,
                                  float* __restrict__ policy, float* __restrict__ value) {
@@ -662,6 +665,7 @@ struct rz_engine {
     cudaStream_t stream2;     // group 1 (tick of one group overlaps the network launch of the other)
     int n_groups;
     int group_slot0[3];
+    int tick_impl;            // 0 = warp-per-game kernel (default), 1 = thread-per-slot cross-check (RZ_TICK_IMPL=thread)
     void* arena[16];
     int n_arena;
     Status* h_status;     // pinned
@@ -734,7 +738,10 @@ static int launch_wave(rz_engine* e) {
         const size_t row0 = (size_t)s0 * c.K, rows = (size_t)(s1 - s0) * c.K;
         if (timed) RZ_CUDA_TRY(cudaEventRecord(ev[0], st));
         RZ_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(uint32_t), st));
-        tick_kernel<<<(s1 - s0 + kTickThreads - 1) / kTickThreads, kTickThreads, 0, st>>>(c, e->dp, s0, s1, g);
+        if (e->tick_impl == 1)
+            tick_kernel<<<(s1 - s0 + kTickThreads - 1) / kTickThreads, kTickThreads, 0, st>>>(c, e->dp, s0, s1, g);
+        else
+            tick_warp_kernel<<<(s1 - s0 + 3) / 4, kWarpTickThreads, 0, st>>>(c, e->dp, s0, s1, g);
         RZ_LAUNCH_CHECK();
         e->mcts_launches++;
         if (timed) RZ_CUDA_TRY(cudaEventRecord(ev[1], st));
@@ -799,6 +806,8 @@ int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net, int device, rz_engin
     e->group_slot0[0] = 0;
     e->group_slot0[1] = e->n_groups == 2 ? (cfg->games + 1) / 2 : cfg->games;
     e->group_slot0[2] = cfg->games;
+    const char* ti = getenv("RZ_TICK_IMPL");
+    e->tick_impl = (ti && strcmp(ti, "thread") == 0) ? 1 : 0;
     DevCfg& c = e->dc;
     c.G = cfg->games; c.S = cfg->simulation_num_per_move; c.K = cfg->parallel_search_num; c.vl = cfg->virtual_loss;
     c.change_tau_turn = cfg->change_tau_turn; c.thinking_loop = cfg->thinking_loop; c.required_visit = cfg->required_visit_to_decide_action;

@@ -1,0 +1,82 @@
+"""End-to-end plumbing test (BASELINE.json config 1 analogue): config/mini.yml's network (16 filters x 1
+block, generic CUDA kernel) and play settings through the SelfPlayWorker mirror on the GPU: play_data files
+in the reference's format (loadable by the trainer's convert_to_training_data logic), GGF lines, game-index
+file, file pruning, and replay parity of every recorded position through the oracle env."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bitboard as ob
+from reversi_zero_b200.config import Config
+from reversi_zero_b200.worker.self_play import SelfPlayWorker
+from reversi_zero_b200.agent.player import ReversiPlayer
+from reversi_zero_b200.env.reversi_env import ReversiEnv, Player
+
+pytestmark = pytest.mark.gpu
+
+
+def mini_config(tmp_path):
+    cfg = Config(project_dir=str(tmp_path), data_dir=str(tmp_path / "data"))
+    # config/mini.yml:3-33 values
+    cfg.model.update(dict(cnn_filter_num=16, cnn_filter_size=3, res_layer_num=1, l2_reg=0.0001, value_fc_size=16))
+    cfg.play.update(dict(simulation_num_per_move=10, share_mtcs_info_in_self_play=True, reset_mtcs_info_per_game=3, thinking_loop=2,
+                         required_visit_to_decide_action=40, start_rethinking_turn=10, c_puct=5, change_tau_turn=10,
+                         parallel_search_num=4, allowed_resign_turn=10, use_solver_turn=0, use_solver_turn_in_simulation=0,
+                         schedule_of_simulation_num_per_move=[[0, 50]]))   # sim_per_move = 50
+    cfg.play_data.update(dict(multi_process_num=1, nb_game_in_file=2, max_file_num=3, save_policy_of_tau_1=True, enable_ggf_data=True,
+                              nb_game_in_ggf_file=2))
+    cfg.b200.games_per_gpu = 8
+    cfg.opts.new = True
+    return cfg
+
+
+def test_mini_selfplay_files(tmp_path):
+    cfg = mini_config(tmp_path)
+    w = SelfPlayWorker(cfg)
+    n = w.start(max_games=10)
+    assert n >= 10
+    files = sorted(glob.glob(os.path.join(cfg.resource.play_data_dir, "play_*.json")))
+    assert 1 <= len(files) <= cfg.play_data.max_file_num        # pruned to max_file_num (self_play.py:209-217)
+    assert int(open(cfg.resource.self_play_game_idx_file).read()) == n
+    assert os.path.exists(cfg.resource.model_best_blob_path)     # `--new` saved the random-init weights
+    n_rec = 0
+    for f in files:
+        data = json.load(open(f))
+        assert len(data) % 8 == 0
+        # the trainer's loader (worker/optimize.py:215-231)
+        for state, policy, z in data:
+            own = ob.bit_to_array(state[0], 64); enemy = ob.bit_to_array(state[1], 64)
+            assert not np.any(own & enemy) and len(policy) == 64 and z in (1, 0, -1)
+            assert abs(sum(policy) - 1) < 1e-9
+            legal = ob.find_correct_moves(state[0], state[1])
+            assert all((legal >> i) & 1 for i, p in enumerate(policy) if p > 0)   # visits only on legal moves
+            n_rec += 1
+        # records 0..7 of a ply are its 8 symmetries in the reference's order (player.py:166-179)
+        o0, e0 = data[0][0]
+        assert data[1][0] == [ob.rotate90(o0), ob.rotate90(e0)] and data[4][0] == [ob.flip_vertical(o0), ob.flip_vertical(e0)]
+    assert n_rec > 0
+    ggf = glob.glob(os.path.join(cfg.resource.self_play_ggf_data_dir, "*.ggf"))
+    assert ggf and all(line.startswith("(;GM[Othello]") for line in open(ggf[0]))
+    st = w.engine.stats()
+    assert st["games_finished"] >= 10 and st["expansions"] > 0
+
+
+def test_reversi_player_mirror_plays_a_game(tmp_path):
+    """ReversiPlayer.action / moves / finish_game contract (agent/player.py:71-134,357-364) driven like
+    worker/evaluate.py:66-96 does."""
+    cfg = mini_config(tmp_path)
+    cfg.play.update(dict(simulation_num_per_move=30, thinking_loop=1, noise_eps=0, change_tau_turn=0, resign_threshold=None))
+    black, white = ReversiPlayer(cfg, None, seed=1), ReversiPlayer(cfg, None, seed=2)   # None -> deterministic evaluator
+    env = ReversiEnv().reset()
+    while not env.done:
+        own, enemy = env.get_own_and_enemy()
+        pl = black if env.next_player == Player.black else white
+        a = pl.action(own, enemy)
+        assert (ob.find_correct_moves(own, enemy) >> a) & 1
+        env.step(a)
+    black.finish_game(1); white.finish_game(-1)
+    assert len(black.moves) % 8 == 0 and black.moves[0][2] == 1 and white.moves[-1][2] == -1
+    assert env.turn <= 60 and env.winner is not None
