@@ -142,6 +142,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--games", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--groups", type=int, default=0, help="engine overlap groups (0 = auto, 1 = no overlap: clean per-kernel timing)")
     ap.add_argument("--full-games", type=int, default=0, metavar="G",
                     help="calibration: play G complete games from a cold start and write gpurun_out/full_games.json")
     args = ap.parse_args()
@@ -189,7 +190,7 @@ def main():
 
     def make_engine():
         cfg = E.engine_cfg_from_play_config(pp, games=args.games, seed=20260922, eval_mode=E.EVAL_NET, first_game_id=rank,
-                                            game_id_stride=world, warm_start=True)
+                                            game_id_stride=world, warm_start=True, overlap_groups=args.groups)
         return E.Engine(cfg, net, local)
 
     if args.full_games:

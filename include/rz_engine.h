@@ -154,6 +154,9 @@ typedef struct rz_engine_cfg {
                                        pre-played plies are not searched and not recorded */
     int32_t overlap_groups;         /* 0 = auto (2 when games >= 256), 1, or 2: slot groups whose MCTS tick overlaps
                                        the other group's network launch on a second stream */
+    int32_t max_sims_per_wave;      /* simulations one game may START in one wave (0 = 2 x parallel_search_num).  Bounds
+                                       the work of a wave for games whose simulations end in terminal positions without
+                                       needing the network (endgame), so no slot delays the whole batch. */
     int32_t max_searches_per_game;  /* sizes the per-game node arena: nodes = this x simulation_num_per_move;
                                        0 = 60 x min(thinking_loop, 2).  Rethinking (thinking_loop > 1) is skipped
                                        when the arena could no longer hold one search per remaining ply. */

@@ -49,6 +49,7 @@ class PlayParams:
         self.disable_resignation_rate = 0.1
         self.share_mtcs_info_in_self_play = True
         self.save_policy_of_tau_1 = True
+        self.max_sims_per_wave = 0  # engine knob (0 = 2 * parallel_search_num): simulations started per game per wave
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise AttributeError(k)
@@ -203,14 +204,17 @@ class SelfPlayGame:
         pp = self.pp
         S, K = pp.simulation_num_per_move, pp.parallel_search_num
         started, parked = 0, []
+        cap = pp.max_sims_per_wave or 2 * K
         while True:
             pending, pending_keys, still_parked = [], set(), []
+            started_wave = 0
             for d in parked:
                 r = self._run(d, pid, pending, pending_keys)
                 if r == "parked":
                     still_parked.append(d)
-            while started < S and len(pending) + len(still_parked) < K:
+            while started < S and len(pending) + len(still_parked) < K and started_wave < cap:
                 started += 1
+                started_wave += 1
                 d = Descent(bb.Env().update(own if pid == 1 else enemy, enemy if pid == 1 else own, pid))
                 r = self._run(d, pid, pending, pending_keys)
                 if r == "parked":

@@ -52,27 +52,57 @@ RZ_HD int ctz64(u64 x) {  // x != 0
 #endif
 }
 
+// Shift policies.  PlainShift is the obvious one.  MulShift (device only) performs the same 64-bit shifts as
+// integer multiply-adds by a power of two held in a kernel parameter (opaque to ptxas, so they are not turned
+// back into SHF): the legal-move kernel is bound by the ALU pipe (LOP3 + SHF, ncu: 91 % active while the FMA
+// pipe idles at 6 %), and IMAD / IMAD.WIDE / IMAD.HI issue on the FMA pipe.
+struct PlainShift {
+    template <int S> RZ_HD u64 l(u64 x) const { return x << S; }
+    template <int S> RZ_HD u64 r(u64 x) const { return x >> S; }
+};
+#if defined(__CUDACC__)
+struct ShiftConsts { uint32_t pow2[33]; };  // pow2[i] = 1u << i (pow2[32] unused)
+struct MulShift {
+    const ShiftConsts& k;
+    template <int S> __device__ __forceinline__ u64 l(u64 x) const {
+        const uint32_t c = k.pow2[S], lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+        const u64 t = (u64)lo * c;                                  // IMAD.WIDE.U32: {lo << S, lo >> (32-S)}
+        const uint32_t h = hi * c + (uint32_t)(t >> 32);            // IMAD
+        return ((u64)h << 32) | (uint32_t)t;
+    }
+    template <int S> __device__ __forceinline__ u64 r(u64 x) const {
+        const uint32_t c = k.pow2[32 - S], lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+        const u64 t = (u64)hi * c;                                  // IMAD.WIDE.U32: {hi << (32-S), hi >> S}
+        const uint32_t l2 = __umulhi(lo, c) + (uint32_t)t;          // IMAD.HI.U32: (lo >> S) | (hi << (32-S))
+        return (t & 0xFFFFFFFF00000000ULL) | l2;
+    }
+};
+#endif
+
 // One direction pair (shift s toward higher and lower bit indices) of the legal-move search.
 // `e` is the opponent mask already restricted so that a shift by s never wraps around a board edge.
 // Kogge-Stone: after the three doubling steps `t` holds every opponent disc that is connected to an
 // own disc through an unbroken run of opponent discs (runs are at most 6 long).
-template <int S>
-RZ_HD u64 mobility_dir(u64 own, u64 e) {
-    u64 up = e & (own << S), dn = e & (own >> S);
-    u64 eu = e & (e << S), ed = e & (e >> S);
-    up |= e & (up << S);          dn |= e & (dn >> S);
-    up |= eu & (up << (2 * S));   dn |= ed & (dn >> (2 * S));
-    up |= eu & (up << (2 * S));   dn |= ed & (dn >> (2 * S));
-    return (up << S) | (dn >> S);
+template <int S, class Sh>
+RZ_HD u64 mobility_dir(u64 own, u64 e, const Sh& sh) {
+    u64 up = e & sh.template l<S>(own), dn = e & sh.template r<S>(own);
+    u64 eu = e & sh.template l<S>(e), ed = e & sh.template r<S>(e);
+    up |= e & sh.template l<S>(up);        dn |= e & sh.template r<S>(dn);
+    up |= eu & sh.template l<2 * S>(up);   dn |= ed & sh.template r<2 * S>(dn);
+    up |= eu & sh.template l<2 * S>(up);   dn |= ed & sh.template r<2 * S>(dn);
+    return sh.template l<S>(up) | sh.template r<S>(dn);
 }
 
-// lib/bitboard.py:53-67: squares where `own` may move.
-RZ_HD u64 find_correct_moves(u64 own, u64 enemy) {
+// lib/bitboard.py:53-67: squares where `own` may move.  ShH / ShV: shift policy for the three directions with a
+// sub-byte stride (1, 7, 9) and for the vertical direction (8).
+template <class ShH, class ShV>
+RZ_HD u64 find_correct_moves_t(u64 own, u64 enemy, const ShH& sh, const ShV& sv) {
     const u64 eh = enemy & kNotEdgeLR;  // horizontal / diagonal runs never include an edge column
-    u64 m = mobility_dir<1>(own, eh) | mobility_dir<7>(own, eh) | mobility_dir<9>(own, eh) |
-            mobility_dir<8>(own, enemy);  // vertical: bits shifted past row 0 / row 7 fall off the word
+    u64 m = mobility_dir<1>(own, eh, sh) | mobility_dir<7>(own, eh, sh) | mobility_dir<9>(own, eh, sh) |
+            mobility_dir<8>(own, enemy, sv);  // vertical: bits shifted past row 0 / row 7 fall off the word
     return m & ~(own | enemy);
 }
+RZ_HD u64 find_correct_moves(u64 own, u64 enemy) { return find_correct_moves_t(own, enemy, PlainShift(), PlainShift()); }
 
 // lib/bitboard.py:84-92: the four rays that run toward higher bit indices from `pos`
 // (down, right, down-left, down-right).  For each ray the carry of (e | ~ray) + 1 ripples through the

@@ -102,7 +102,7 @@ struct Status {
 
 struct DevCfg {
     int G, S, K, vl, change_tau_turn, thinking_loop, required_visit, start_rethinking_turn, allowed_resign_turn;
-    int use_resign, share, max_plies, warm_start;
+    int use_resign, share, max_plies, warm_start, sims_cap;
     float c_puct, noise_eps, alpha, resign_threshold, disable_resignation_rate;
     u64 seed, first_game_id, game_id_stride, max_games;
     uint32_t nodes_cap, edges_cap, hash_cap;  // per slot (hash_cap is a power of two)
@@ -356,6 +356,7 @@ struct Ctx {
         while (true) {
             uint8_t still[kMaxK];
             int n_still = 0;
+            int started_wave = 0;
             sl.n_pending = 0;
             for (int j = 0; j < sl.n_parked; ++j) {
                 const int di = sl.parked[j];
@@ -364,8 +365,9 @@ struct Ctx {
                 else if (r == 1) { desc[di].status = D_PENDING; sl.pending[sl.n_pending++] = (uint8_t)di; }
                 else desc[di].status = D_FREE;
             }
-            while (sl.sims_started < sl.sims_target && sl.n_pending + n_still < c.K) {
+            while (sl.sims_started < sl.sims_target && sl.n_pending + n_still < c.K && started_wave < c.sims_cap) {
                 int di = 0;
+                ++started_wave;
                 while (desc[di].status != D_FREE) ++di;
                 sl.sims_started++;
                 start_descent(di);
@@ -379,6 +381,7 @@ struct Ctx {
             for (int j = 0; j < n_still; ++j) sl.parked[j] = still[j];
             if (sl.n_pending > 0) return true;
             if (sl.sims_started >= sl.sims_target) return false;
+            return true;  // cap reached with nothing to evaluate: continue in the next wave
         }
     }
 
@@ -741,7 +744,7 @@ static int launch_wave(rz_engine* e) {
         if (e->tick_impl == 1)
             tick_kernel<<<(s1 - s0 + kTickThreads - 1) / kTickThreads, kTickThreads, 0, st>>>(c, e->dp, s0, s1, g);
         else
-            tick_warp_kernel<<<(s1 - s0 + 3) / 4, kWarpTickThreads, 0, st>>>(c, e->dp, s0, s1, g);
+            tick_warp_kernel<<<(s1 - s0 + 1) / 2, kWarpTickThreads, 0, st>>>(c, e->dp, s0, s1, g);
         RZ_LAUNCH_CHECK();
         e->mcts_launches++;
         if (timed) RZ_CUDA_TRY(cudaEventRecord(ev[1], st));
@@ -814,6 +817,7 @@ int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net, int device, rz_engin
     c.start_rethinking_turn = cfg->start_rethinking_turn; c.allowed_resign_turn = cfg->allowed_resign_turn;
     c.use_resign = cfg->use_resign_threshold; c.share = cfg->share_mtcs_info; c.max_plies = cfg->max_plies > 0 ? cfg->max_plies : 64;
     c.warm_start = cfg->warm_start;
+    c.sims_cap = cfg->max_sims_per_wave > 0 ? cfg->max_sims_per_wave : 2 * cfg->parallel_search_num;
     c.c_puct = cfg->c_puct; c.noise_eps = cfg->noise_eps; c.alpha = cfg->dirichlet_alpha; c.resign_threshold = cfg->resign_threshold;
     c.disable_resignation_rate = cfg->disable_resignation_rate;
     c.seed = cfg->seed; c.first_game_id = cfg->first_game_id; c.game_id_stride = cfg->game_id_stride; c.max_games = cfg->max_games;

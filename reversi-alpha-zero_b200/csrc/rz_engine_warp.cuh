@@ -282,6 +282,7 @@ struct WCtx {
         while (true) {
             uint8_t still[kMaxK];
             int n_still = 0;
+            int started_wave = 0;
             sl.n_pending = 0;
             for (int j = 0; j < sl.n_parked; ++j) {
                 const int di = sl.parked[j];
@@ -290,8 +291,9 @@ struct WCtx {
                 else if (r == 1) { dstat[di] = D_PENDING; sl.pending[sl.n_pending++] = (uint8_t)di; }
                 else dstat[di] = D_FREE;
             }
-            while (sl.sims_started < sl.sims_target && sl.n_pending + n_still < c.K) {
+            while (sl.sims_started < sl.sims_target && sl.n_pending + n_still < c.K && started_wave < c.sims_cap) {
                 int di = 0;
+                ++started_wave;
                 while (dstat[di] != D_FREE) ++di;
                 sl.sims_started++;
                 start_descent(di);
@@ -305,6 +307,7 @@ struct WCtx {
             for (int j = 0; j < n_still; ++j) sl.parked[j] = still[j];
             if (sl.n_pending > 0) return true;
             if (sl.sims_started >= sl.sims_target) return false;
+            return true;  // cap reached with nothing to evaluate: continue in the next wave
         }
     }
 
@@ -461,7 +464,7 @@ struct WCtx {
     }
 };
 
-constexpr int kWarpTickThreads = 128;  // 4 game slots per CTA
+constexpr int kWarpTickThreads = 64;  // 2 game slots per CTA: 64 x 124 registers fit beside a resident tower CTA (320 x 168)
 
 __global__ void __launch_bounds__(kWarpTickThreads) tick_warp_kernel(const DevCfg c, const DevPtrs p, const int slot0, const int slot_end,
                                                                      const int group) {

@@ -5,6 +5,7 @@
 // coalesced run; each thread handles two consecutive positions through 128-bit loads/stores, inputs
 // are streamed with ld.global.nc.L1::no_allocate, outputs with st.global.cs.  Grids are a multiple of
 // the SM count (persistent grid-stride loop).
+#include <stdlib.h>
 #include "rz_bitboard.cuh"
 #include "rz_common.cuh"
 
@@ -26,15 +27,25 @@ __device__ __forceinline__ void stg_stream_u64x2(u64* p, u64 a, u64 b) {
 
 constexpr int kThreads = 256;
 
+// MODE 0: all shifts on the ALU pipe; 1: sub-byte-stride directions via IMAD (FMA pipe); 2: all via IMAD
+template <int MODE>
+__device__ __forceinline__ u64 fcm_balanced(u64 own, u64 enemy, const ShiftConsts& k) {
+    if (MODE == 0) return find_correct_moves(own, enemy);
+    const MulShift ms{k};
+    if (MODE == 1) return find_correct_moves_t(own, enemy, ms, PlainShift());
+    return find_correct_moves_t(own, enemy, ms, ms);
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(kThreads) k1_find_correct_moves(const u64* __restrict__ own, const u64* __restrict__ enemy,
-                                                                  u64* __restrict__ out, size_t n, int vec_ok) {
+                                                                  u64* __restrict__ out, size_t n, int vec_ok, const ShiftConsts k) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (vec_ok) {
         const size_t pairs = n >> 1;
         for (size_t i = tid; i < pairs; i += stride) {
             ulonglong2 o = ldg_stream_u64x2(own + 2 * i), e = ldg_stream_u64x2(enemy + 2 * i);
-            stg_stream_u64x2(out + 2 * i, find_correct_moves(o.x, e.x), find_correct_moves(o.y, e.y));
+            stg_stream_u64x2(out + 2 * i, fcm_balanced<MODE>(o.x, e.x, k), fcm_balanced<MODE>(o.y, e.y, k));
         }
         if ((n & 1) && tid == 0) out[n - 1] = find_correct_moves(own[n - 1], enemy[n - 1]);
     } else {
@@ -114,7 +125,14 @@ int rz_find_correct_moves_dev(const uint64_t* own, const uint64_t* enemy, uint64
     RZ_REQUIRE(n == 0 || (own && enemy && out), "rz_find_correct_moves_dev: null pointer");
     if (n == 0) return RZ_OK;
     const int vec = aligned16(own) && aligned16(enemy) && aligned16(out);
-    k1_find_correct_moves<<<grid_for(vec ? (n + 1) / 2 : n), kThreads, 0, (cudaStream_t)stream>>>(own, enemy, out, n, vec);
+    ShiftConsts k;
+    for (int i = 0; i < 33; ++i) k.pow2[i] = i < 32 ? (1u << i) : 0u;
+    static int mode = -1;
+    if (mode < 0) { const char* m = getenv("RZ_K1_SHIFT_MODE"); mode = m ? atoi(m) : 1; if (mode < 0 || mode > 2) mode = 1; }
+    const int grid = grid_for(vec ? (n + 1) / 2 : n);
+    if (mode == 0) k1_find_correct_moves<0><<<grid, kThreads, 0, (cudaStream_t)stream>>>(own, enemy, out, n, vec, k);
+    else if (mode == 1) k1_find_correct_moves<1><<<grid, kThreads, 0, (cudaStream_t)stream>>>(own, enemy, out, n, vec, k);
+    else k1_find_correct_moves<2><<<grid, kThreads, 0, (cudaStream_t)stream>>>(own, enemy, out, n, vec, k);
     RZ_LAUNCH_CHECK();
     return RZ_OK;
 }

@@ -32,6 +32,7 @@ def engine_cfg_from_play_config(pc, pdc=None, games=1024, seed=0, eval_mode=EVAL
     cfg.warm_start = 1 if warm_start else 0
     cfg.overlap_groups = overlap_groups
     cfg.max_searches_per_game = max_searches_per_game
+    cfg.max_sims_per_wave = int(getattr(pc, "max_sims_per_wave", 0) or 0)
     cfg.c_puct = float(pc.c_puct)
     cfg.noise_eps = float(pc.noise_eps)
     cfg.dirichlet_alpha = float(pc.dirichlet_alpha)
