@@ -81,12 +81,15 @@ def expansions_per_game():
     """mean network evaluations per COMPLETE game of this workload, measured on the B200 engine by
     `bench.py --full-games` (cold start, every game played from the first to the last ply) and committed under
     profiles/; the fallback is the value probed on the reference (21 256 at sim = 400)."""
+    sims = PLAY_KW["simulation_num_per_move"]
     try:
         with open(os.path.join(ROOT, "profiles", "full_games.json")) as f:
             d = json.load(f)
-        return float(d["expansions_per_game"]), "measured: profiles/full_games.json (%d complete games)" % d["games"]
+        if "sims=%d " % sims in d["workload"]:
+            return float(d["expansions_per_game"]), "measured: profiles/full_games.json (%d complete games)" % d["games"]
+        return float(d["expansions_per_game"]) * sims / 400.0, "ESTIMATE: profiles/full_games.json (sims=400) scaled by sims/400"
     except Exception:
-        return 21256.0, "fallback: reference probe, SURVEY 3.1"
+        return 21256.0 * sims / 400.0, "fallback: reference probe at sim=400 (SURVEY 3.1), scaled by sims/400"
 
 
 def cpu_baseline(budget_s, processes=None, torch_threads=1):
@@ -125,8 +128,8 @@ def run_reference(args):
 
 
 def workload_config(args, **extra):
-    c = dict(workload="selfplay ch5 net (256x10, random-init) G=%d games/GPU sims=400 K=8 c_puct=5 vl=3 noise=0.25 tau_turn=4 "
-                      "thinking_loop=1 solver=off resign=off" % args.games,
+    c = dict(workload="selfplay ch5 net (256x10, random-init) G=%d games/GPU sims=%d K=8 c_puct=5 vl=3 noise=0.25 tau_turn=4 "
+                      "thinking_loop=1 solver=off resign=off" % (args.games, args.sims),
              games_per_gpu=args.games, simulation_num_per_move=PLAY_KW["simulation_num_per_move"],
              l2="leaf batch + per-game trees (>20 GB) exceed L2; weights (23.7 MB fp16) are L2-resident by design",
              step="one wave = MCTS tick kernel + tcgen05 tower launch over the leaf batch", parallelism=f"dp{args.gpus} (games sharded by rank)")
@@ -142,10 +145,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--games", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sims", type=int, default=400, help="simulation_num_per_move (BASELINE config 3 uses 800 with --games 8192)")
     ap.add_argument("--groups", type=int, default=0, help="engine overlap groups (0 = auto, 1 = no overlap: clean per-kernel timing)")
     ap.add_argument("--full-games", type=int, default=0, metavar="G",
                     help="calibration: play G complete games from a cold start and write gpurun_out/full_games.json")
     args = ap.parse_args()
+    PLAY_KW["simulation_num_per_move"] = args.sims
     if args.impl == "reference":
         if args.steps > 4:
             args.steps, args.warmup = 2, 0  # each step is a 12 s time-bounded CPU sample (+ process start-up)

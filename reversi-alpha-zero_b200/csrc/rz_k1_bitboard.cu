@@ -128,7 +128,7 @@ int rz_find_correct_moves_dev(const uint64_t* own, const uint64_t* enemy, uint64
     ShiftConsts k;
     for (int i = 0; i < 33; ++i) k.pow2[i] = i < 32 ? (1u << i) : 0u;
     static int mode = -1;
-    if (mode < 0) { const char* m = getenv("RZ_K1_SHIFT_MODE"); mode = m ? atoi(m) : 1; if (mode < 0 || mode > 2) mode = 1; }
+    if (mode < 0) { const char* m = getenv("RZ_K1_SHIFT_MODE"); mode = m ? atoi(m) : 0; if (mode < 0 || mode > 2) mode = 0; }
     const int grid = grid_for(vec ? (n + 1) / 2 : n);
     if (mode == 0) k1_find_correct_moves<0><<<grid, kThreads, 0, (cudaStream_t)stream>>>(own, enemy, out, n, vec, k);
     else if (mode == 1) k1_find_correct_moves<1><<<grid, kThreads, 0, (cudaStream_t)stream>>>(own, enemy, out, n, vec, k);

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.join(ROOT, "reversi-alpha-zero_b200"))
 FLOP_PER_POS = 2 * 755_343_616
 
 
-def run(n=32768, iters=5, warmup=2):
+def run(n=32768, iters=5, warmup=2, res_blocks=10):
     import torch
     from reversi_zero_b200.agent import model as M
     from reversi_zero_b200 import net as N, device as D
@@ -20,7 +20,8 @@ def run(n=32768, iters=5, warmup=2):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    mc = M.ModelConfig()
+    mc = M.ModelConfig(res_layer_num=res_blocks)
+    flop = 2 * (64 * 256 * 18 + res_blocks * 2 * 64 * 256 * 2304 + 64 * 3 * 256 + 128 * 64 + 64 * 256 + 256)
     net = N.Net(mc)
     net.load_weights(M.build_random_weights(mc, 0))
     rng = np.random.default_rng(0)
@@ -38,11 +39,12 @@ def run(n=32768, iters=5, warmup=2):
     e1.record(s)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
-    tflops = n * FLOP_PER_POS / ms / 1e9
-    return dict(n=n, ms=ms, pos_per_s=n / ms * 1e3, tflops=tflops, frac_of_burst_peak=tflops / peaks.get("bf16_tflops", 1590.0),
+    tflops = n * flop / ms / 1e9
+    return dict(n=n, res_blocks=res_blocks, flop_per_position=flop, ms=ms, pos_per_s=n / ms * 1e3, tflops=tflops, frac_of_burst_peak=tflops / peaks.get("bf16_tflops", 1590.0),
                 frac_of_sustained_peak=tflops / peaks.get("bf16_tflops_sustained", 1400.0))
 
 
 if __name__ == "__main__":
+    rb = int(sys.argv[1]) if len(sys.argv) > 1 else 10
     for n in (296, 32768):
-        print(json.dumps(run(n)))
+        print(json.dumps(run(n, res_blocks=rb)))
