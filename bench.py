@@ -236,6 +236,17 @@ def main():
     run_ms = d["run_ms"]
     eng.poll()
     eng.close()
+    # roofline leg: the same workload with ONE slot group, so that the CUDA events around each tower launch bracket
+    # exactly that kernel (with two groups a launch's events also contain the wait for the other group's launch)
+    cfg1 = E.engine_cfg_from_play_config(pp, games=args.games, seed=20260922, eval_mode=E.EVAL_NET, first_game_id=rank,
+                                         game_id_stride=world, warm_start=True, overlap_groups=1)
+    eng1 = E.Engine(cfg1, net, local)
+    eng1.run(max_waves=args.warmup)
+    r0 = eng1.stats()
+    eng1.run(max_waves=max(24, args.steps // 5))
+    r1 = eng1.stats()
+    eng1.close()
+    roof = {k: r1[k] - r0[k] for k in r1}
     counts = torch.tensor([d["games_finished"], d["expansions"], d["simulations"], d["plies"], d["nn_launches"] + d["mcts_launches"]],
                           dtype=torch.float64, device=f"cuda:{local}")
     tmax = torch.tensor([run_ms, d["nn_ms"], d["mcts_ms"]], dtype=torch.float64, device=f"cuda:{local}")
@@ -307,9 +318,9 @@ def main():
         return
 
     # ---- roofline of the dominant kernel (the tcgen05 tower): algorithmic flop / device time of its launches ----
-    nn_launches = d["nn_launches"]
-    rank_exps = d["expansions"]
-    achieved = rank_exps * FLOP_PER_EXPANSION / (d["nn_ms"] / 1e3) / 1e12 if d["nn_ms"] > 0 else 0.0
+    nn_launches = roof["nn_launches"]
+    rank_exps = roof["expansions"]
+    achieved = rank_exps * FLOP_PER_EXPANSION / (roof["nn_ms"] / 1e3) / 1e12 if roof["nn_ms"] > 0 else 0.0
     peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1400.0))  # kernel timed inside a long step
     traffic = None
     try:
@@ -318,9 +329,10 @@ def main():
         pass
     roofline = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic,
                     peak_source=f"{pk_src} bf16_tflops_sustained", kernel="net_tower_kernel",
-                    launches=nn_launches, avg_launch_ms=d["nn_ms"] / max(1, nn_launches),
-                    mean_leaf_batch=rank_exps / max(1, nn_launches), share_of_step=d["nn_ms"] / max(1e-9, d["run_ms"]),
-                    mcts_tick_share_of_step=d["mcts_ms"] / max(1e-9, d["run_ms"]))
+                    launches=nn_launches, avg_launch_ms=roof["nn_ms"] / max(1, nn_launches),
+                    mean_leaf_batch=rank_exps / max(1, nn_launches), share_of_step=roof["nn_ms"] / max(1e-9, roof["run_ms"]),
+                    mcts_tick_share_of_step=roof["mcts_ms"] / max(1e-9, roof["run_ms"]),
+                    measured_on="a second engine with overlap_groups=1 right after the timed region (events bracket single launches)")
 
     cb = None
     if not args.no_cpu_baseline:

@@ -53,28 +53,34 @@ RZ_HD int ctz64(u64 x) {  // x != 0
 }
 
 // Shift policies.  PlainShift is the obvious one.  MulShift (device only) performs the same 64-bit shifts as
-// integer multiply-adds by a power of two held in a kernel parameter (opaque to ptxas, so they are not turned
-// back into SHF): the legal-move kernel is bound by the ALU pipe (LOP3 + SHF, ncu: 91 % active while the FMA
-// pipe idles at 6 %), and IMAD / IMAD.WIDE / IMAD.HI issue on the FMA pipe.
+// 32-bit integer multiply-adds by a power of two held in a kernel parameter (opaque to ptxas, so they are not
+// turned back into SHF): the legal-move kernel is bound by the ALU pipe (LOP3 + SHF; ncu: 91 % active while the
+// FMA pipe idles at 6 %), and IMAD / IMAD.HI issue on the FMA pipe, so moving part of the shifts balances the two.
 struct PlainShift {
     template <int S> RZ_HD u64 l(u64 x) const { return x << S; }
     template <int S> RZ_HD u64 r(u64 x) const { return x >> S; }
 };
 #if defined(__CUDACC__)
 struct ShiftConsts { uint32_t pow2[33]; };  // pow2[i] = 1u << i (pow2[32] unused)
+// LM / RM: do the left / right shifts on the FMA pipe.  With c = 2^S (left) or 2^(32-S) (right):
+//   x << S : lo' = lo << S,  hi' = hi * c + mulhi(lo, c)          (IMAD.SHL, IMAD.HI, IMAD)
+//   x >> S : hi' = mulhi(hi, c),  lo' = mulhi(lo, c) + hi * c      (IMAD.HI, IMAD.HI, IMAD)
+template <bool LM, bool RM>
 struct MulShift {
     const ShiftConsts& k;
+    __device__ __forceinline__ static void split(u64 x, uint32_t& lo, uint32_t& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(x)); }
+    __device__ __forceinline__ static u64 join(uint32_t lo, uint32_t hi) { u64 x; asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "r"(lo), "r"(hi)); return x; }
     template <int S> __device__ __forceinline__ u64 l(u64 x) const {
-        const uint32_t c = k.pow2[S], lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
-        const u64 t = (u64)lo * c;                                  // IMAD.WIDE.U32: {lo << S, lo >> (32-S)}
-        const uint32_t h = hi * c + (uint32_t)(t >> 32);            // IMAD
-        return ((u64)h << 32) | (uint32_t)t;
+        if (!LM) return x << S;
+        uint32_t lo, hi; split(x, lo, hi);
+        const uint32_t c = k.pow2[S];
+        return join(lo << S, hi * c + __umulhi(lo, c));
     }
     template <int S> __device__ __forceinline__ u64 r(u64 x) const {
-        const uint32_t c = k.pow2[32 - S], lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
-        const u64 t = (u64)hi * c;                                  // IMAD.WIDE.U32: {hi << (32-S), hi >> S}
-        const uint32_t l2 = __umulhi(lo, c) + (uint32_t)t;          // IMAD.HI.U32: (lo >> S) | (hi << (32-S))
-        return (t & 0xFFFFFFFF00000000ULL) | l2;
+        if (!RM) return x >> S;
+        uint32_t lo, hi; split(x, lo, hi);
+        const uint32_t c = k.pow2[32 - S];
+        return join(__umulhi(lo, c) + hi * c, __umulhi(hi, c));
     }
 };
 #endif
@@ -93,13 +99,12 @@ RZ_HD u64 mobility_dir(u64 own, u64 e, const Sh& sh) {
     return sh.template l<S>(up) | sh.template r<S>(dn);
 }
 
-// lib/bitboard.py:53-67: squares where `own` may move.  ShH / ShV: shift policy for the three directions with a
-// sub-byte stride (1, 7, 9) and for the vertical direction (8).
-template <class ShH, class ShV>
-RZ_HD u64 find_correct_moves_t(u64 own, u64 enemy, const ShH& sh, const ShV& sv) {
+// lib/bitboard.py:53-67: squares where `own` may move.  ShA: shift policy for the directions 1 and 9, ShB for 7 and 8.
+template <class ShA, class ShB>
+RZ_HD u64 find_correct_moves_t(u64 own, u64 enemy, const ShA& sa, const ShB& sb) {
     const u64 eh = enemy & kNotEdgeLR;  // horizontal / diagonal runs never include an edge column
-    u64 m = mobility_dir<1>(own, eh, sh) | mobility_dir<7>(own, eh, sh) | mobility_dir<9>(own, eh, sh) |
-            mobility_dir<8>(own, enemy, sv);  // vertical: bits shifted past row 0 / row 7 fall off the word
+    u64 m = mobility_dir<1>(own, eh, sa) | mobility_dir<7>(own, eh, sb) | mobility_dir<9>(own, eh, sa) |
+            mobility_dir<8>(own, enemy, sb);  // vertical: bits shifted past row 0 / row 7 fall off the word
     return m & ~(own | enemy);
 }
 RZ_HD u64 find_correct_moves(u64 own, u64 enemy) { return find_correct_moves_t(own, enemy, PlainShift(), PlainShift()); }

@@ -27,13 +27,14 @@ __device__ __forceinline__ void stg_stream_u64x2(u64* p, u64 a, u64 b) {
 
 constexpr int kThreads = 256;
 
-// MODE 0: all shifts on the ALU pipe; 1: sub-byte-stride directions via IMAD (FMA pipe); 2: all via IMAD
+// MODE 0: all shifts on the ALU pipe (SHF); 1: right shifts on the FMA pipe; 2: right shifts + the left shifts of
+// directions 1 and 9 on the FMA pipe; 3: every shift on the FMA pipe
 template <int MODE>
 __device__ __forceinline__ u64 fcm_balanced(u64 own, u64 enemy, const ShiftConsts& k) {
     if (MODE == 0) return find_correct_moves(own, enemy);
-    const MulShift ms{k};
-    if (MODE == 1) return find_correct_moves_t(own, enemy, ms, PlainShift());
-    return find_correct_moves_t(own, enemy, ms, ms);
+    if (MODE == 1) return find_correct_moves_t(own, enemy, MulShift<false, true>{k}, MulShift<false, true>{k});
+    if (MODE == 2) return find_correct_moves_t(own, enemy, MulShift<true, true>{k}, MulShift<false, true>{k});
+    return find_correct_moves_t(own, enemy, MulShift<true, true>{k}, MulShift<true, true>{k});
 }
 
 template <int MODE>
@@ -128,11 +129,12 @@ int rz_find_correct_moves_dev(const uint64_t* own, const uint64_t* enemy, uint64
     ShiftConsts k;
     for (int i = 0; i < 33; ++i) k.pow2[i] = i < 32 ? (1u << i) : 0u;
     static int mode = -1;
-    if (mode < 0) { const char* m = getenv("RZ_K1_SHIFT_MODE"); mode = m ? atoi(m) : 0; if (mode < 0 || mode > 2) mode = 0; }
+    if (mode < 0) { const char* m = getenv("RZ_K1_SHIFT_MODE"); mode = m ? atoi(m) : 0; if (mode < 0 || mode > 3) mode = 0; }
     const int grid = grid_for(vec ? (n + 1) / 2 : n);
     if (mode == 0) k1_find_correct_moves<0><<<grid, kThreads, 0, (cudaStream_t)stream>>>(own, enemy, out, n, vec, k);
     else if (mode == 1) k1_find_correct_moves<1><<<grid, kThreads, 0, (cudaStream_t)stream>>>(own, enemy, out, n, vec, k);
-    else k1_find_correct_moves<2><<<grid, kThreads, 0, (cudaStream_t)stream>>>(own, enemy, out, n, vec, k);
+    else if (mode == 2) k1_find_correct_moves<2><<<grid, kThreads, 0, (cudaStream_t)stream>>>(own, enemy, out, n, vec, k);
+    else k1_find_correct_moves<3><<<grid, kThreads, 0, (cudaStream_t)stream>>>(own, enemy, out, n, vec, k);
     RZ_LAUNCH_CHECK();
     return RZ_OK;
 }
