@@ -52,62 +52,29 @@ RZ_HD int ctz64(u64 x) {  // x != 0
 #endif
 }
 
-// Shift policies.  PlainShift is the obvious one.  MulShift (device only) performs the same 64-bit shifts as
-// 32-bit integer multiply-adds by a power of two held in a kernel parameter (opaque to ptxas, so they are not
-// turned back into SHF): the legal-move kernel is bound by the ALU pipe (LOP3 + SHF; ncu: 91 % active while the
-// FMA pipe idles at 6 %), and IMAD / IMAD.HI issue on the FMA pipe, so moving part of the shifts balances the two.
-struct PlainShift {
-    template <int S> RZ_HD u64 l(u64 x) const { return x << S; }
-    template <int S> RZ_HD u64 r(u64 x) const { return x >> S; }
-};
-#if defined(__CUDACC__)
-struct ShiftConsts { uint32_t pow2[33]; };  // pow2[i] = 1u << i (pow2[32] unused)
-// LM / RM: do the left / right shifts on the FMA pipe.  With c = 2^S (left) or 2^(32-S) (right):
-//   x << S : lo' = lo << S,  hi' = hi * c + mulhi(lo, c)          (IMAD.SHL, IMAD.HI, IMAD)
-//   x >> S : hi' = mulhi(hi, c),  lo' = mulhi(lo, c) + hi * c      (IMAD.HI, IMAD.HI, IMAD)
-template <bool LM, bool RM>
-struct MulShift {
-    const ShiftConsts& k;
-    __device__ __forceinline__ static void split(u64 x, uint32_t& lo, uint32_t& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(x)); }
-    __device__ __forceinline__ static u64 join(uint32_t lo, uint32_t hi) { u64 x; asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "r"(lo), "r"(hi)); return x; }
-    template <int S> __device__ __forceinline__ u64 l(u64 x) const {
-        if (!LM) return x << S;
-        uint32_t lo, hi; split(x, lo, hi);
-        const uint32_t c = k.pow2[S];
-        return join(lo << S, hi * c + __umulhi(lo, c));
-    }
-    template <int S> __device__ __forceinline__ u64 r(u64 x) const {
-        if (!RM) return x >> S;
-        uint32_t lo, hi; split(x, lo, hi);
-        const uint32_t c = k.pow2[32 - S];
-        return join(__umulhi(lo, c) + hi * c, __umulhi(hi, c));
-    }
-};
-#endif
-
-// One direction pair (shift s toward higher and lower bit indices) of the legal-move search.
-// `e` is the opponent mask already restricted so that a shift by s never wraps around a board edge.
-// Kogge-Stone: after the three doubling steps `t` holds every opponent disc that is connected to an
+// One direction pair (shift S toward higher and lower bit indices) of the legal-move search.
+// `e` is the opponent mask already restricted so that a shift by S never wraps around a board edge.
+// Kogge-Stone: after the three doubling steps `up` / `dn` hold every opponent disc that is connected to an
 // own disc through an unbroken run of opponent discs (runs are at most 6 long).
-template <int S, class Sh>
-RZ_HD u64 mobility_dir(u64 own, u64 e, const Sh& sh) {
-    u64 up = e & sh.template l<S>(own), dn = e & sh.template r<S>(own);
-    u64 eu = e & sh.template l<S>(e), ed = e & sh.template r<S>(e);
-    up |= e & sh.template l<S>(up);        dn |= e & sh.template r<S>(dn);
-    up |= eu & sh.template l<2 * S>(up);   dn |= ed & sh.template r<2 * S>(dn);
-    up |= eu & sh.template l<2 * S>(up);   dn |= ed & sh.template r<2 * S>(dn);
-    return sh.template l<S>(up) | sh.template r<S>(dn);
+template <int S>
+RZ_HD u64 mobility_dir(u64 own, u64 e) {
+    u64 up = e & (own << S), dn = e & (own >> S);
+    u64 eu = e & (e << S), ed = e & (e >> S);
+    up |= e & (up << S);          dn |= e & (dn >> S);
+    up |= eu & (up << (2 * S));   dn |= ed & (dn >> (2 * S));
+    up |= eu & (up << (2 * S));   dn |= ed & (dn >> (2 * S));
+    return (up << S) | (dn >> S);
 }
 
-// lib/bitboard.py:53-67: squares where `own` may move.  ShA: shift policy for the directions 1 and 9, ShB for 7 and 8.
-template <class ShA, class ShB>
-RZ_HD u64 find_correct_moves_t(u64 own, u64 enemy, const ShA& sa, const ShB& sb) {
+// lib/bitboard.py:53-67: squares where `own` may move.
+// (Moving the 64-bit shifts to the FMA pipe as IMAD / IMAD.HI by powers of two was tried and measured slower,
+// profiles/k1_shift_modes_r01.json.)
+RZ_HD u64 find_correct_moves(u64 own, u64 enemy) {
     const u64 eh = enemy & kNotEdgeLR;  // horizontal / diagonal runs never include an edge column
-    u64 m = mobility_dir<1>(own, eh, sa) | mobility_dir<7>(own, eh, sb) | mobility_dir<9>(own, eh, sa) |
-            mobility_dir<8>(own, enemy, sb);  // vertical: bits shifted past row 0 / row 7 fall off the word
+    u64 m = mobility_dir<1>(own, eh) | mobility_dir<7>(own, eh) | mobility_dir<9>(own, eh) |
+            mobility_dir<8>(own, enemy);  // vertical: bits shifted past row 0 / row 7 fall off the word
     return m & ~(own | enemy);
 }
-RZ_HD u64 find_correct_moves(u64 own, u64 enemy) { return find_correct_moves_t(own, enemy, PlainShift(), PlainShift()); }
 
 // lib/bitboard.py:84-92: the four rays that run toward higher bit indices from `pos`
 // (down, right, down-left, down-right).  For each ray the carry of (e | ~ray) + 1 ripples through the

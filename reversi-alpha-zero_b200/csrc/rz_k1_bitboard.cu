@@ -27,26 +27,15 @@ __device__ __forceinline__ void stg_stream_u64x2(u64* p, u64 a, u64 b) {
 
 constexpr int kThreads = 256;
 
-// MODE 0: all shifts on the ALU pipe (SHF); 1: right shifts on the FMA pipe; 2: right shifts + the left shifts of
-// directions 1 and 9 on the FMA pipe; 3: every shift on the FMA pipe
-template <int MODE>
-__device__ __forceinline__ u64 fcm_balanced(u64 own, u64 enemy, const ShiftConsts& k) {
-    if (MODE == 0) return find_correct_moves(own, enemy);
-    if (MODE == 1) return find_correct_moves_t(own, enemy, MulShift<false, true>{k}, MulShift<false, true>{k});
-    if (MODE == 2) return find_correct_moves_t(own, enemy, MulShift<true, true>{k}, MulShift<false, true>{k});
-    return find_correct_moves_t(own, enemy, MulShift<true, true>{k}, MulShift<true, true>{k});
-}
-
-template <int MODE>
 __global__ void __launch_bounds__(kThreads) k1_find_correct_moves(const u64* __restrict__ own, const u64* __restrict__ enemy,
-                                                                  u64* __restrict__ out, size_t n, int vec_ok, const ShiftConsts k) {
+                                                                  u64* __restrict__ out, size_t n, int vec_ok) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (vec_ok) {
         const size_t pairs = n >> 1;
         for (size_t i = tid; i < pairs; i += stride) {
             ulonglong2 o = ldg_stream_u64x2(own + 2 * i), e = ldg_stream_u64x2(enemy + 2 * i);
-            stg_stream_u64x2(out + 2 * i, fcm_balanced<MODE>(o.x, e.x, k), fcm_balanced<MODE>(o.y, e.y, k));
+            stg_stream_u64x2(out + 2 * i, find_correct_moves(o.x, e.x), find_correct_moves(o.y, e.y));
         }
         if ((n & 1) && tid == 0) out[n - 1] = find_correct_moves(own[n - 1], enemy[n - 1]);
     } else {
@@ -126,15 +115,7 @@ int rz_find_correct_moves_dev(const uint64_t* own, const uint64_t* enemy, uint64
     RZ_REQUIRE(n == 0 || (own && enemy && out), "rz_find_correct_moves_dev: null pointer");
     if (n == 0) return RZ_OK;
     const int vec = aligned16(own) && aligned16(enemy) && aligned16(out);
-    ShiftConsts k;
-    for (int i = 0; i < 33; ++i) k.pow2[i] = i < 32 ? (1u << i) : 0u;
-    static int mode = -1;
-    if (mode < 0) { const char* m = getenv("RZ_K1_SHIFT_MODE"); mode = m ? atoi(m) : 0; if (mode < 0 || mode > 3) mode = 0; }
-    const int grid = grid_for(vec ? (n + 1) / 2 : n);
-    if (mode == 0) k1_find_correct_moves<0><<<grid, kThreads, 0, (cudaStream_t)stream>>>(own, enemy, out, n, vec, k);
-    else if (mode == 1) k1_find_correct_moves<1><<<grid, kThreads, 0, (cudaStream_t)stream>>>(own, enemy, out, n, vec, k);
-    else if (mode == 2) k1_find_correct_moves<2><<<grid, kThreads, 0, (cudaStream_t)stream>>>(own, enemy, out, n, vec, k);
-    else k1_find_correct_moves<3><<<grid, kThreads, 0, (cudaStream_t)stream>>>(own, enemy, out, n, vec, k);
+    k1_find_correct_moves<<<grid_for(vec ? (n + 1) / 2 : n), kThreads, 0, (cudaStream_t)stream>>>(own, enemy, out, n, vec);
     RZ_LAUNCH_CHECK();
     return RZ_OK;
 }

@@ -138,11 +138,35 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
         : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait::ld that also carries a register dependency on the loaded values, so the compiler cannot schedule a use of
+// v[] above the wait (tcgen05.ld completes asynchronously)
+__device__ __forceinline__ void tmem_wait_ld_dep(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+                   "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                   "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_dep(uint32_t (&v)[32]) {
+    asm volatile(""
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+                   "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                   "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// two fp32 -> packed fp16x2 (a in the low half), saturating at +-65504; RELU folds max(x, 0) into the convert
+template <bool RELU>
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-    __half2 h = __floats2half2_rn(fminf(a, 65504.f), fminf(b, 65504.f));  // inputs are >= 0 (post-ReLU)
-    return *reinterpret_cast<uint32_t*>(&h);
+    uint32_t d;
+    if (RELU) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    else      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
 }
 
 struct Params {
@@ -316,33 +340,47 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_kernel(const Params pp)
                 const bool is_conv2 = l > 0 && (l & 1) == 0;   // second conv of a block: add the skip connection
                 const bool keep_res = l == 0 || is_conv2;      // block output: keep fp32 copy in TMEM
                 const bool last = l == L - 1;
-#pragma unroll 1
-                for (int c4 = 0; c4 < 4; ++c4) {
+                // 4 chunks of 32 accumulator columns per thread; the TMEM load of chunk c+1 is in flight while chunk c
+                // is processed (tcgen05.wait::ld only after the math and the stores of chunk c).
+                uint32_t va[32], vb[32], rr[32];
+                auto prefetch = [&](int c4, uint32_t (&v)[32], uint32_t (&r)[32]) {
                     const int c0 = h * 128 + c4 * 32;
-                    uint32_t v[32];
                     tmem_ld32(tm_acc + lane_sel + c0, v);
+                    if (is_conv2) tmem_ld32(tm_res + lane_sel + c0, r);
+                };
+                auto math = [&](int c4, uint32_t (&v)[32], uint32_t (&r)[32]) {
+                    const int c0 = h * 128 + c4 * 32;
                     if (is_conv2) {
-                        uint32_t r[32];
-                        tmem_ld32(tm_res + lane_sel + c0, r);
-                        tmem_wait_ld();
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             v[j] = __float_as_uint(fmaxf(fmaf(__uint_as_float(v[j]), sc[c0 + j], sc[256 + c0 + j]) + __uint_as_float(r[j]), 0.f));
-                    } else {
-                        tmem_wait_ld();
+                    } else if (keep_res || last) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             v[j] = __float_as_uint(fmaxf(fmaf(__uint_as_float(v[j]), sc[c0 + j], sc[256 + c0 + j]), 0.f));
+                    } else {  // first conv of a block: only the fp16 operand is needed, ReLU happens in the convert
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), sc[c0 + j], sc[256 + c0 + j]));
                     }
+                };
+                auto store = [&](int c4, uint32_t (&v)[32]) {
+                    const int c0 = h * 128 + c4 * 32;
                     if (keep_res && !last) tmem_st32(tm_res + lane_sel + c0, v);
                     if (!last) {
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj) {
                             uint4 pk;
-                            pk.x = pack_h2(__uint_as_float(v[jj * 8 + 0]), __uint_as_float(v[jj * 8 + 1]));
-                            pk.y = pack_h2(__uint_as_float(v[jj * 8 + 2]), __uint_as_float(v[jj * 8 + 3]));
-                            pk.z = pack_h2(__uint_as_float(v[jj * 8 + 4]), __uint_as_float(v[jj * 8 + 5]));
-                            pk.w = pack_h2(__uint_as_float(v[jj * 8 + 6]), __uint_as_float(v[jj * 8 + 7]));
+                            if (keep_res) {
+                                pk.x = pack_h2<false>(__uint_as_float(v[jj * 8 + 0]), __uint_as_float(v[jj * 8 + 1]));
+                                pk.y = pack_h2<false>(__uint_as_float(v[jj * 8 + 2]), __uint_as_float(v[jj * 8 + 3]));
+                                pk.z = pack_h2<false>(__uint_as_float(v[jj * 8 + 4]), __uint_as_float(v[jj * 8 + 5]));
+                                pk.w = pack_h2<false>(__uint_as_float(v[jj * 8 + 6]), __uint_as_float(v[jj * 8 + 7]));
+                            } else {
+                                pk.x = pack_h2<true>(__uint_as_float(v[jj * 8 + 0]), __uint_as_float(v[jj * 8 + 1]));
+                                pk.y = pack_h2<true>(__uint_as_float(v[jj * 8 + 2]), __uint_as_float(v[jj * 8 + 3]));
+                                pk.z = pack_h2<true>(__uint_as_float(v[jj * 8 + 4]), __uint_as_float(v[jj * 8 + 5]));
+                                pk.w = pack_h2<true>(__uint_as_float(v[jj * 8 + 6]), __uint_as_float(v[jj * 8 + 7]));
+                            }
                             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(act_row + ((c0 >> 3) + jj) * kActCg), "r"(pk.x),
                                          "r"(pk.y), "r"(pk.z), "r"(pk.w)
                                          : "memory");
@@ -365,7 +403,17 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_kernel(const Params pp)
                             for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]);
                         }
                     }
-                }
+                };
+                // the residual buffer rr is consumed by math(c) before prefetch(c+1) refills it
+                prefetch(0, va, rr);
+                tmem_wait_ld_dep(va); if (is_conv2) tmem_dep(rr);
+                math(0, va, rr); prefetch(1, vb, rr); store(0, va);
+                tmem_wait_ld_dep(vb); if (is_conv2) tmem_dep(rr);
+                math(1, vb, rr); prefetch(2, va, rr); store(1, vb);
+                tmem_wait_ld_dep(va); if (is_conv2) tmem_dep(rr);
+                math(2, va, rr); prefetch(3, vb, rr); store(2, va);
+                tmem_wait_ld_dep(vb); if (is_conv2) tmem_dep(rr);
+                math(3, vb, rr); store(3, vb);
                 if (!last) {
                     if (keep_res) tmem_wait_st();
                     fence_proxy_async();
