@@ -54,8 +54,7 @@ def _b200(config):
 def load_or_build_weights(config, net):
     """agent/api.py:102-115 load_model: best weights if present, else build() + save_as_best (``--new``).
     The engine-side hand-off file is a float32 .npy blob (h5 import from the Keras trainer: SURVEY 8(f).1)."""
-    rc = config.resource
-    path = getattr(rc, "model_best_blob_path", os.path.join(rc.model_dir, "model_best_weight.rzblob.npy"))
+    path = blob_path_of(config)
     if not getattr(config.opts, "new", False) and os.path.exists(path):
         blob = np.load(path)
         logger.debug(f"loading weights from {path}")
@@ -68,7 +67,14 @@ def load_or_build_weights(config, net):
     return blob
 
 
+def blob_path_of(config):
+    rc = config.resource
+    return getattr(rc, "model_best_blob_path", os.path.join(rc.model_dir, "model_best_weight.rzblob.npy"))
+
+
 class SelfPlayWorker:
+    MODEL_CHECK_INTERVAL_SEC = 60  # agent/api.py:80-82
+
     def __init__(self, config, env=None, api=None, shared_var=None, worker_index=0, net=None, device=0, rank=0,
                  world_size=1):
         """env / api / shared_var are accepted for signature compatibility with the reference
@@ -90,6 +96,7 @@ class SelfPlayWorker:
         self.local_idx = 0
         self.game_idx = 0
         self.files_written = []
+        self.last_model_check_time = time.time()
 
     # -- reference helpers ---------------------------------------------------------------------------------
     def decide_simulation_num_per_move(self, idx):
@@ -123,6 +130,40 @@ class SelfPlayWorker:
         self.resign_test_game_count = 0
         self.engine.set_resign_threshold(pc.resign_threshold)
 
+    def try_reload_model(self, force_check=False):
+        """agent/api.py:117-125 + lib/model_helpler.py digest logic: every 60 s look at the weight hand-off file
+        and, if its sha256 differs from the loaded weights, load it between two waves.  With several ranks, rank 0
+        decides and broadcasts flag + blob (NCCL), so that all GPUs switch at the same harvest point."""
+        if not force_check and time.time() - self.last_model_check_time < self.MODEL_CHECK_INTERVAL_SEC:
+            return False
+        self.last_model_check_time = time.time()
+        path = blob_path_of(self.config)
+        blob = None
+        changed = False
+        if self.rank == 0 and os.path.exists(path):
+            try:
+                blob = np.load(path)
+                changed = blob.size == self.net.blob_floats and M.blob_digest(blob) != self.net.digest
+            except Exception as e:  # partially written file: try again at the next check
+                logger.error(e)
+        if self.world_size > 1:
+            import torch
+            import torch.distributed as dist
+            from ..parallel import broadcast_blob
+            flag = torch.tensor([1 if changed else 0], dtype=torch.int32, device=f"cuda:{self.device}")
+            dist.broadcast(flag, src=0)
+            if not int(flag.item()):
+                return False
+            t = broadcast_blob(self.config.model, blob, f"cuda:{self.device}")
+            torch.cuda.synchronize()
+            self.net.load_blob_dev(t)
+            self.net.digest = M.blob_digest(t.cpu().numpy())
+            return True
+        if changed:
+            self.net.load_blob(blob)
+            logger.debug(f"reloaded weights, digest = {self.net.digest}")
+        return changed
+
     # -- engine plumbing ------------------------------------------------------------------------------------
     def _make_engine(self):
         cfg, b = self.config, _b200(self.config)
@@ -152,6 +193,7 @@ class SelfPlayWorker:
                 target = min(target, max_games)
             self.engine.run(finished_target=self.local_idx + (target - finished))
             finished += self._harvest()
+            self.try_reload_model()
             if max_games is not None and finished >= max_games:
                 break
             if max_seconds is not None and time.time() - t0 >= max_seconds:

@@ -68,3 +68,27 @@ def test_float_repr_edge_cases(tmp_path):
         assert data[8 * i][1] == list(pol)          # identity symmetry first (agent/player.py:166-179)
         for v in pol[:2]:
             assert repr(float(v)) in text
+
+
+def test_reference_trainer_loads_our_files(tmp_path):
+    """a play_data file written by the C-ABI writer goes through the UNMODIFIED reference's
+    read_game_data_from_file + OptimizeWorker.convert_to_training_data (worker/optimize.py:215-231).  Runs only where
+    the reference checkout exists (the build container)."""
+    import oracle.ref_shims.install as shims
+    if not shims.available():
+        pytest.skip("reference sources not present")
+    shims.install()
+    from reversi_zero.lib.data_helper import read_game_data_from_file
+    from reversi_zero.worker.optimize import OptimizeWorker
+    pp = mcts.PlayParams(simulation_num_per_move=20, parallel_search_num=4, noise_eps=0.25, c_puct=5)
+    games = [mcts.SelfPlayGame(pp, onn.FakeNetAPI(), seed=5, game_id=i).play() for i in range(2)]
+    G, P = to_ctypes(games)
+    path = str(tmp_path / "play_20260922-000000.000000.json")
+    n = E.write_play_data(path, G, len(games), P, True, 4)
+    data = read_game_data_from_file(path)
+    states, policies, zs = OptimizeWorker.convert_to_training_data(data)
+    assert states.shape == (n, 2, 8, 8) and policies.shape == (n, 64) and zs.shape == (n,)
+    assert states.dtype == np.uint8 and set(np.unique(zs)) <= {-1, 0, 1}
+    assert np.allclose(policies.sum(axis=1), 1.0)
+    # first record = first ply of black from the start position, identity symmetry
+    assert states[0, 0].sum() == 2 and states[0, 1].sum() == 2 and states[0, 0, 3, 4] == 1

@@ -62,6 +62,17 @@ def test_mini_selfplay_files(tmp_path):
     assert ggf and all(line.startswith("(;GM[Othello]") for line in open(ggf[0]))
     st = w.engine.stats()
     assert st["games_finished"] >= 10 and st["expansions"] > 0
+    # weight hot reload (agent/api.py:117-125): a new blob in the hand-off file is picked up by digest
+    from reversi_zero_b200.agent import model as M
+    old = w.net.digest
+    assert not w.try_reload_model(force_check=True)
+    planes = np.zeros((1, 2, 8, 8), np.uint8); planes[0, 0, 3, 4] = planes[0, 1, 3, 3] = 1
+    p_old, _ = w.net.predict_planes(planes)
+    np.save(cfg.resource.model_best_blob_path, M.weights_to_blob(cfg.model, M.build_random_weights(cfg.model, 99)))
+    assert w.try_reload_model(force_check=True) and w.net.digest != old
+    p_new, _ = w.net.predict_planes(planes)
+    assert np.abs(p_new - p_old).max() > 1e-6
+    assert w.start(max_games=2) >= 2      # keeps playing with the new weights
 
 
 def test_reversi_player_mirror_plays_a_game(tmp_path):
