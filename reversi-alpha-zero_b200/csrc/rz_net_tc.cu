@@ -21,6 +21,7 @@
 //     from the two bitboards; the policy / value heads run on the epilogue warps from the fp32 tower
 //     output.
 // HBM traffic per position: 16 B in, 260 B out.  Algorithmic work: 2 * 755,343,616 flop.
+#include <stdlib.h>
 #include "rz_bitboard.cuh"
 #include "rz_net.cuh"
 
@@ -90,6 +91,26 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                  "r"(bytes), "r"(bar)
                  : "memory");
+}
+// multicast variants (thread-block cluster): the copy lands at the same CTA-relative offset in every CTA of
+// `mask` and signals the mbarrier at the same offset there; the commit arrives on every CTA's barrier
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -187,6 +208,11 @@ struct Params {
     int V;
 };
 
+// CL = thread-block-cluster size (1 or 2).  With CL = 2 the two CTAs of a cluster each fetch half of every weight
+// stage from L2 and multicast it into both CTAs' shared memory (L2 -> SM weight traffic halves); MMAs, TMEM and the
+// epilogue stay per-CTA (cta_group::1).  A stage may be refilled only after BOTH CTAs' MMAs have read it, so the
+// `empty` barriers count CL commits (each MMA thread commits to every CTA of the cluster).
+template <int CL>
 __global__ void __launch_bounds__(kThreads, 1) net_tower_kernel(const Params pp) {
     Params p = pp;
     if (p.n_dev) p.n = *p.n_dev;
@@ -200,12 +226,18 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_kernel(const Params pp)
     const uint32_t bar_w0 = bar0 + 2 * kStages * 8, bar_a = bar_w0 + 8, bar_acc = bar_w0 + 16;
     const uint32_t ntiles = (p.n + 1) >> 1;
     const int L = p.n_layers;
+    // every CTA of a cluster runs the same number of tile iterations (the producers / MMA threads are coupled through
+    // the shared weight ring); a CTA whose last tile index is past the batch processes an all-empty dummy tile
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+    const uint32_t cbase = blockIdx.x - crank;
+    const uint32_t iters = cbase < ntiles ? (ntiles - cbase + gridDim.x - 1) / gridDim.x : 0u;
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
     // ---- one-time setup -----------------------------------------------------------------------------
     for (uint32_t i = threadIdx.x * 16; i < kActBytes; i += kThreads * 16) *reinterpret_cast<uint4*>(sm + kOffAct + i) = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     if (threadIdx.x == 0) {
-        for (uint32_t s = 0; s < kStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+        for (uint32_t s = 0; s < kStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), CL); }
         mbar_init(bar_w0, 1);
         mbar_init(bar_a, kEpiThreads);
         mbar_init(bar_acc, 1);
@@ -217,6 +249,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_kernel(const Params pp)
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts into them
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + kOffTmemPtr);
     const uint32_t tm_acc = tmem, tm_res = tmem + 256;
@@ -227,13 +260,19 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_kernel(const Params pp)
             mbar_expect_tx(bar_w0, kW0Bytes);
             bulk_g2s(base + kOffW0, p.w0, kW0Bytes, bar_w0);
             uint32_t stage = 0, phase = 0;
-            for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (uint32_t it = 0; it < iters; ++it) {
                 for (int l = 1; l < L; ++l) {
                     const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w) + (size_t)(l - 1) * 36 * kStageBytes;
                     for (int s = 0; s < 36; ++s) {
                         mbar_wait(bar_empty(stage), phase ^ 1);
                         mbar_expect_tx(bar_full(stage), kStageBytes);
-                        bulk_g2s(base + kOffW + stage * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes, bar_full(stage));
+                        if (CL == 1) {
+                            bulk_g2s(base + kOffW + stage * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes, bar_full(stage));
+                        } else {  // this CTA's slice of the stage, delivered to every CTA of the cluster
+                            constexpr uint32_t kSlice = kStageBytes / CL;
+                            bulk_g2s_mc(base + kOffW + stage * kStageBytes + crank * kSlice, src + (size_t)s * kStageBytes + crank * kSlice,
+                                        kSlice, bar_full(stage), kMask);
+                        }
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -244,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_kernel(const Params pp)
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, a_par = 0;
             bool first = true;
-            for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (uint32_t it = 0; it < iters; ++it) {
                 for (int l = 0; l < L; ++l) {
                     mbar_wait(bar_a, a_par);
                     a_par ^= 1;
@@ -267,7 +306,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_kernel(const Params pp)
                                 for (uint32_t j = 0; j < 4; ++j)
                                     umma_f16(tm_acc, smem_desc(a_tap + (kb * 8 + 2 * j) * kActCg, kActCg, kActSlot),
                                              smem_desc(b_st + 2 * j * 4096, 4096, 128), kIdesc, (tap | kb | j) != 0);
-                                umma_commit(bar_empty(stage));
+                                if (CL == 1) umma_commit(bar_empty(stage)); else umma_commit_mc(bar_empty(stage), kMask);
                                 if (++stage == kStages) { stage = 0; phase ^= 1; }
                             }
                         }
@@ -295,7 +334,8 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_kernel(const Params pp)
         uint32_t acc_par = 0;
         uint32_t ss_buf = 0;
 
-        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (uint32_t it = 0; it < iters; ++it) {
+            const uint32_t tile = blockIdx.x + it * gridDim.x;  // may be >= ntiles: dummy tile (no valid board)
             const uint32_t pos0 = tile * 2;
             const bool valid = pos0 + brd < p.n;
             // ---- layer-0 operand: im2col of the two bit planes, K index = tap*2 + plane, padded to 32 ----
@@ -483,6 +523,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_kernel(const Params pp)
 
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it / arrive on its barriers
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
@@ -520,10 +561,12 @@ int net_forward_tc(rz_net* net, const uint64_t* own, const uint64_t* enemy, floa
     RZ_REQUIRE(net->cfg.filters == 256, "tcgen05 tower requires 256 filters");
     RZ_REQUIRE(net->cfg.value_fc <= (int)tc::kMaxV, "tcgen05 tower supports value_fc_size <= %u", tc::kMaxV);
     RZ_REQUIRE(n < (1ull << 31), "batch too large");
-    static bool attr_set = false;
-    if (!attr_set) {
-        RZ_CUDA_TRY(cudaFuncSetAttribute(tc::net_tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemAlloc));
-        attr_set = true;
+    static int cluster = -1;
+    if (cluster < 0) {
+        const char* cs = getenv("RZ_TOWER_CLUSTER");
+        cluster = (cs && atoi(cs) == 1) ? 1 : 2;
+        RZ_CUDA_TRY(cudaFuncSetAttribute(tc::net_tower_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemAlloc));
+        RZ_CUDA_TRY(cudaFuncSetAttribute(tc::net_tower_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemAlloc));
     }
     tc::Params p;
     p.w0 = net->tc_w0; p.w = net->tc_w; p.ss = net->scale_shift; p.blob = net->blob;
@@ -533,8 +576,19 @@ int net_forward_tc(rz_net* net, const uint64_t* own, const uint64_t* enemy, floa
     p.own = own; p.enemy = enemy; p.policy = policy; p.value = value; p.dbg_tower = dbg_tower;
     p.n = (uint32_t)n; p.n_dev = n_dev; p.n_layers = 1 + 2 * net->cfg.res_blocks; p.V = net->cfg.value_fc;
     const uint32_t ntiles = (uint32_t)((n + 1) / 2);
-    const uint32_t grid = ntiles < (uint32_t)num_sms() ? ntiles : (uint32_t)num_sms();
-    tc::net_tower_kernel<<<grid, tc::kThreads, tc::kSmemAlloc, stream>>>(p);
+    uint32_t grid = ntiles < (uint32_t)num_sms() ? ntiles : (uint32_t)num_sms();
+    if (cluster == 1) {
+        tc::net_tower_kernel<1><<<grid, tc::kThreads, tc::kSmemAlloc, stream>>>(p);
+    } else {
+        grid = (grid + 1) & ~1u;  // whole clusters; a surplus CTA runs dummy tiles
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc::kThreads); cfg.dynamicSmemBytes = tc::kSmemAlloc; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        RZ_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::net_tower_kernel<2>, p));
+    }
     RZ_LAUNCH_CHECK();
     return RZ_OK;
 }
