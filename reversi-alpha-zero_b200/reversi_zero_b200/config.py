@@ -57,60 +57,37 @@ class ResourceConfig(_Section):
             os.makedirs(d, exist_ok=True)
 
 
-class ModelConfig(_Section):
-    """config.py:187-193"""
+# field -> default, per section; values are the reference's (config.py:116-193)
+_MODEL = dict(cnn_filter_num=256, cnn_filter_size=3, res_layer_num=10, l2_reg=1e-4, value_fc_size=256)          # :187-193
+_PLAY = dict(                                                                                                     # :128-166
+    simulation_num_per_move=200, share_mtcs_info_in_self_play=True, reset_mtcs_info_per_game=1, thinking_loop=10,
+    required_visit_to_decide_action=400, start_rethinking_turn=8, c_puct=1, noise_eps=0.25, dirichlet_alpha=0.5,
+    change_tau_turn=4, virtual_loss=3, prediction_queue_size=16, parallel_search_num=8, prediction_worker_sleep_sec=0.0001,
+    wait_for_expanding_sleep_sec=0.00001, resign_threshold=-0.9, allowed_resign_turn=20, disable_resignation_rate=0.1,
+    false_positive_threshold=0.05, resign_threshold_delta=0.01, policy_decay_turn=60, policy_decay_power=3,
+    use_solver_turn=50, use_solver_turn_in_simulation=50, use_newest_next_generation_model=True)
+_PLAY_DATA = dict(multi_process_num=16, nb_game_in_file=2, max_file_num=800, save_policy_of_tau_1=True,           # :116-125
+                  enable_ggf_data=True, nb_game_in_ggf_file=100, drop_draw_game_rate=0)
 
-    def __init__(self):
-        self.cnn_filter_num = 256
-        self.cnn_filter_size = 3
-        self.res_layer_num = 10
-        self.l2_reg = 1e-4
-        self.value_fc_size = 256
+
+def _section(name, defaults, doc):
+    def init(self):
+        for k, v in defaults.items():
+            setattr(self, k, v)
+    return type(name, (_Section,), {"__init__": init, "__doc__": doc})
+
+
+ModelConfig = _section("ModelConfig", _MODEL, "network shape, config.py:187-193")
+PlayDataConfig = _section("PlayDataConfig", _PLAY_DATA, "play-data files, config.py:116-125")
 
 
 class PlayConfig(_Section):
-    """config.py:128-166"""
+    """MCTS / move-choice parameters, config.py:128-166"""
 
     def __init__(self):
-        self.simulation_num_per_move = 200
-        self.share_mtcs_info_in_self_play = True
-        self.reset_mtcs_info_per_game = 1
-        self.thinking_loop = 10
-        self.required_visit_to_decide_action = 400
-        self.start_rethinking_turn = 8
-        self.c_puct = 1
-        self.noise_eps = 0.25
-        self.dirichlet_alpha = 0.5
-        self.change_tau_turn = 4
-        self.virtual_loss = 3
-        self.prediction_queue_size = 16
-        self.parallel_search_num = 8
-        self.prediction_worker_sleep_sec = 0.0001
-        self.wait_for_expanding_sleep_sec = 0.00001
-        self.resign_threshold = -0.9
-        self.allowed_resign_turn = 20
-        self.disable_resignation_rate = 0.1
-        self.false_positive_threshold = 0.05
-        self.resign_threshold_delta = 0.01
-        self.policy_decay_turn = 60
-        self.policy_decay_power = 3
-        self.use_solver_turn = 50
-        self.use_solver_turn_in_simulation = 50
+        for k, v in _PLAY.items():
+            setattr(self, k, v)
         self.schedule_of_simulation_num_per_move = [(0, 8), (300, 50), (2000, 200)]
-        self.use_newest_next_generation_model = True
-
-
-class PlayDataConfig(_Section):
-    """config.py:116-125"""
-
-    def __init__(self):
-        self.multi_process_num = 16
-        self.nb_game_in_file = 2
-        self.max_file_num = 800
-        self.save_policy_of_tau_1 = True
-        self.enable_ggf_data = True
-        self.nb_game_in_ggf_file = 100
-        self.drop_draw_game_rate = 0
 
 
 class B200Config(_Section):
