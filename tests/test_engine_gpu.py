@@ -142,3 +142,33 @@ def test_warp_and_thread_tick_kernels_agree():
         for g in gs:
             replay_check(g)
     assert out["warp"] == out["thread"]
+
+
+def test_search_with_real_network_matches_oracle():
+    """Integration of the pieces the deterministic evaluator cannot exercise: the dihedral transform of the leaf
+    batch (K3), the network, and the inverse-dihedral policy gather + re-normalisation at expansion.  mini.yml-sized
+    network on the fp32 generic kernel (2e-5 from torch): visit counts must be identical in almost every slot; a
+    last-bit difference in a prior may flip one arg-max, so a small fraction of slots may differ slightly."""
+    from reversi_zero_b200.agent import model as M
+    from reversi_zero_b200 import net as N
+    mc = M.ModelConfig(cnn_filter_num=16, res_layer_num=1, value_fc_size=16)
+    w = M.build_random_weights(mc, 4, perturb_bn=True)
+    net = N.Net(mc)
+    net.load_weights(w)
+    pp = params(simulation_num_per_move=48, parallel_search_num=4, noise_eps=0.0)
+    cfg = E.engine_cfg_from_play_config(pp, games=24, seed=31, eval_mode=E.EVAL_NET, net_impl=N.IMPL_GENERIC)
+    eng = E.Engine(cfg, net)
+    own, enemy = 0x00000000081d0603, 0x0002043814020100
+    same, dist = 0, []
+    for slot in range(24):
+        n, _ = eng.search_root(own, enemy, 1, slot)
+        game = mcts.SelfPlayGame(pp, onn.OracleNetAPI(w, 1), seed=31, game_id=slot)
+        game.search(own, enemy, 1)
+        ref = game.table[(own, enemy)].N
+        assert n.sum() == ref.sum()
+        same += int(list(n) == list(ref))
+        dist.append(np.abs(n - ref).sum())
+    assert same >= 20, (same, dist)
+    assert max(dist) <= 12, dist
+    eng.close()
+    net.close()
