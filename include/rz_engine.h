@@ -197,7 +197,8 @@ typedef struct rz_game {
     uint8_t resign_enabled;
     uint8_t resigned_mask;  /* bit0 black wanted to resign, bit1 white */
     uint8_t turn;           /* ReversiEnv.turn at the end */
-    uint8_t pad[3];
+    uint8_t black_net;      /* evaluation matches: 0 = black was played by the first network, 1 = by the second */
+    uint8_t pad[2];
 } rz_game;
 
 typedef struct rz_stats {
@@ -225,6 +226,13 @@ int rz_engine_stats(rz_engine* e, rz_stats* out);
 /* change the per-move simulation count for games started from now on
  * (SelfPlayWorker.decide_simulation_num_per_move, worker/self_play.py:262-272). */
 int rz_engine_set_simulation_num(rz_engine* e, int32_t sims);
+/* evaluation matches (worker/evaluate.py:44-96: best model vs challenger): with a second network set, the game with
+ * local index i is played by the first network as black when i is even and by the second when i is odd (the
+ * reference draws the colours at random, :70), and every search is evaluated by the mover's own network.  Use
+ * share_mtcs_info = 0 (the reference gives each evaluation player its own statistics).  RZ_EVAL_FAKE: the "second
+ * network" is the deterministic evaluator with the value negated.  NULL switches back to one network.  Call before
+ * the first rz_engine_run. */
+int rz_engine_set_second_net(rz_engine* e, rz_net* net_b, int enable);
 /* update the resignation rule for decisions taken from now on (SelfPlayWorker's threshold auto-tuner,
  * worker/self_play.py:250-260). */
 int rz_engine_set_resign_threshold(rz_engine* e, int use_resign_threshold, float resign_threshold);

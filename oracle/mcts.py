@@ -133,8 +133,12 @@ class SelfPlayGame:
     """One self-play game: both players, shared (or separate) statistics, compact per-ply log."""
     deadline = None  # optional wall-clock bound used by the CPU-baseline timing (oracle/selfplay_cpu.py)
 
-    def __init__(self, pp, api, seed=0, game_id=0, noise_rng=None):
+    def __init__(self, pp, api, seed=0, game_id=0, noise_rng=None, api_b=None, black_net=0):
+        """api_b / black_net: evaluation matches (worker/evaluate.py:66-96) -- the player of colour `pid` is
+        evaluated by `api` when it plays for network 0 and by `api_b` when it plays for network 1; black_net says
+        which network has the black stones."""
         self.pp, self.api, self.seed, self.game_id = pp, api, seed, game_id
+        self.api_b, self.black_net = api_b, black_net
         self.noise_rng = noise_rng or np.random.default_rng((seed, game_id))
         self.env = bb.Env().reset()
         self.table = {}
@@ -239,7 +243,8 @@ class SelfPlayGame:
         sh = np.arange(64, dtype=np.uint64)
         planes = np.stack([((t_own[:, None] >> sh) & np.uint64(1)), ((t_en[:, None] >> sh) & np.uint64(1))],
                           axis=1).astype(np.uint8).reshape(-1, 2, 8, 8)
-        policy, value = self.api.predict(planes)
+        net = 0 if self.api_b is None else (self.black_net if pid == 1 else 1 - self.black_net)
+        policy, value = (self.api_b if net else self.api).predict(planes)
         for i, (d, key, own, enemy, t, mover_is_root) in enumerate(pending):
             node = self.table.get(key)
             if node is None:

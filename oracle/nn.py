@@ -83,9 +83,11 @@ class FakeNetAPI:
     """Deterministic, dihedral-invariant stand-in used for exact MCTS parity tests (reference, oracle
     and CUDA engine all implement it): policy = 1/64 everywhere, value = (#own - #enemy)/64."""
 
-    def __init__(self):
+    def __init__(self, sign=1.0):
+        """sign = -1: the engine's deterministic "second network" of evaluation matches (value negated)."""
         self.rows = 0
         self.calls = 0
+        self.sign = np.float32(sign)
 
     def predict(self, x):
         x = np.asarray(x)
@@ -95,7 +97,7 @@ class FakeNetAPI:
         n = x.shape[0]
         p = np.full((n, 64), 1.0 / 64, dtype=np.float32)
         cnt = x.reshape(n, 2, 64).astype(np.int32).sum(axis=2)
-        v = ((cnt[:, 0] - cnt[:, 1]).astype(np.float32) / np.float32(64)).reshape(n, 1)
+        v = (self.sign * ((cnt[:, 0] - cnt[:, 1]).astype(np.float32) / np.float32(64))).reshape(n, 1)
         self.rows += n
         self.calls += 1
         return (p[0], v[0]) if single else (p, v)

@@ -90,7 +90,7 @@ struct Slot {
     uint8_t resigned_mask, search_only, n_pending, n_parked;
     uint8_t pending[kMaxK], parked[kMaxK];
     u64 root_own, root_enemy;
-    uint8_t root_pid, pad[7];
+    uint8_t root_pid, black_net, cur_net, pad[5];  // black_net / cur_net: evaluation matches (two networks)
 };
 
 struct Status {
@@ -102,7 +102,7 @@ struct Status {
 
 struct DevCfg {
     int G, S, K, vl, change_tau_turn, thinking_loop, required_visit, start_rethinking_turn, allowed_resign_turn;
-    int use_resign, share, max_plies, warm_start, sims_cap;
+    int use_resign, share, max_plies, warm_start, sims_cap, two_nets;
     float c_puct, noise_eps, alpha, resign_threshold, disable_resignation_rate;
     u64 seed, first_game_id, game_id_stride, max_games;
     uint32_t nodes_cap, edges_cap, hash_cap;  // per slot (hash_cap is a power of two)
@@ -387,6 +387,7 @@ struct Ctx {
 
     __device__ void begin_search(u64 own, u64 enemy, int pid) {
         sl.root_own = own; sl.root_enemy = enemy; sl.root_pid = (uint8_t)pid;
+        sl.cur_net = c.two_nets ? (uint8_t)(pid == 1 ? sl.black_net : 1 - sl.black_net) : (uint8_t)0;
         sl.sims_started = 0; sl.sims_target = (uint32_t)c.S;
         sl.n_pending = 0; sl.n_parked = 0;
         sl.phase = PH_SEARCH;
@@ -400,6 +401,7 @@ struct Ctx {
             return;
         }
         sl.game_id = c.first_game_id + local * c.game_id_stride;
+        sl.black_net = c.two_nets ? (uint8_t)(local & 1) : (uint8_t)0;
         sl.games_played++;
         env_reset(sl.env);
         sl.gen = sl.gen + 1;
@@ -437,6 +439,7 @@ struct Ctx {
         g.first_ply = 0; g.n_plies = (int32_t)sl.ply; g.expansions = (int32_t)sl.n_expand; g.simulations = (int32_t)sl.n_sims;
         g.winner = sl.env.winner; g.black_z = sl.env.winner == 1 ? 1 : (sl.env.winner == 2 ? -1 : 0);
         g.resign_enabled = sl.enable_resign; g.resigned_mask = sl.resigned_mask; g.turn = sl.env.turn;
+        g.black_net = sl.black_net; g.pad[0] = g.pad[1] = 0;
         atomicMax(&p.status->max_nodes, (unsigned long long)sl.n_nodes);
         atomicMax(&p.status->max_edges, (unsigned long long)sl.n_edges);
         __threadfence();
@@ -582,13 +585,16 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const DevCfg c, cons
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     uint32_t base = 0;
-    if (lane == 31 && total > 0) base = atomicAdd(p.batch_count + group * 64, (uint32_t)total);
+    if (!c.two_nets && lane == 31 && total > 0) base = atomicAdd(p.batch_count + group * 64, (uint32_t)total);
     base = __shfl_sync(0xffffffffu, base, 31);
     if (n_leaves > 0) {
         Slot& sl = p.slots[s];
         Descent* desc = p.desc + (size_t)s * c.K;
-        // each group owns the batch rows [slot0 * K, slot_end * K); leaf_index is the absolute row
+        // each (network, group) owns the batch rows [net * G * K + slot0 * K, ...); leaf_index is the absolute row
         uint32_t at = (uint32_t)slot0 * (uint32_t)c.K + base + (uint32_t)(incl - n_leaves);
+        if (c.two_nets)  // slots of one warp may belong to different networks: one atomic per slot
+            at = (uint32_t)sl.cur_net * (uint32_t)c.G * (uint32_t)c.K + (uint32_t)slot0 * (uint32_t)c.K +
+                 atomicAdd(p.batch_count + (sl.cur_net * 2 + group) * 64, (uint32_t)n_leaves);
         for (int j = 0; j < n_leaves; ++j, ++at) {
             Descent& d = desc[sl.pending[j]];
             d.leaf_index = at;
@@ -602,11 +608,11 @@ __global__ void __launch_bounds__(kTickThreads) tick_kernel(const DevCfg c, cons
 
 // RZ_EVAL_FAKE: policy 1/64, value (#own - #enemy)/64 (oracle/nn.py FakeNetAPI)
 __global__ void fake_eval_kernel(const u64* __restrict__ own, const u64* __restrict__ enemy, const uint32_t* __restrict__ count,
-                                 float* __restrict__ policy, float* __restrict__ value) {
+                                 float* __restrict__ policy, float* __restrict__ value, float sign) {
     const uint32_t n = *count;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n * 64; i += gridDim.x * blockDim.x) {
         policy[i] = 1.0f / 64.0f;
-        if ((i & 63) == 0) value[i >> 6] = (float)(popc64(own[i >> 6]) - popc64(enemy[i >> 6])) / 64.0f;
+        if ((i & 63) == 0) value[i >> 6] = sign * ((float)(popc64(own[i >> 6]) - popc64(enemy[i >> 6])) / 64.0f);
     }
 }
 
@@ -663,6 +669,7 @@ struct rz_engine {
     DevCfg dc;
     DevPtrs dp;
     rz_net* net;
+    rz_net* net_b;  // evaluation matches: the second network (NULL in self-play)
     int device;
     cudaStream_t stream;      // group 0 + all host<->device traffic
     cudaStream_t stream2;     // group 1 (tick of one group overlaps the network launch of the other)
@@ -737,10 +744,9 @@ static int launch_wave(rz_engine* e) {
         cudaStream_t st = g == 0 ? e->stream : e->stream2;
         const int s0 = e->group_slot0[g], s1 = e->group_slot0[g + 1];
         cudaEvent_t* ev = e->ev + (g * 8 + e->ev_used) * 3;
-        uint32_t* count = e->dp.batch_count + g * 64;
-        const size_t row0 = (size_t)s0 * c.K, rows = (size_t)(s1 - s0) * c.K;
+        const size_t rows = (size_t)(s1 - s0) * c.K;
         if (timed) RZ_CUDA_TRY(cudaEventRecord(ev[0], st));
-        RZ_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(uint32_t), st));
+        for (int net = 0; net <= c.two_nets; ++net) RZ_CUDA_TRY(cudaMemsetAsync(e->dp.batch_count + (net * 2 + g) * 64, 0, sizeof(uint32_t), st));
         if (e->tick_impl == 1)
             tick_kernel<<<(s1 - s0 + kTickThreads - 1) / kTickThreads, kTickThreads, 0, st>>>(c, e->dp, s0, s1, g);
         else
@@ -748,15 +754,19 @@ static int launch_wave(rz_engine* e) {
         RZ_LAUNCH_CHECK();
         e->mcts_launches++;
         if (timed) RZ_CUDA_TRY(cudaEventRecord(ev[1], st));
-        if (e->cfg.eval_mode == RZ_EVAL_FAKE) {
-            fake_eval_kernel<<<num_sms() * 4, 256, 0, st>>>(e->dp.batch_own + row0, e->dp.batch_enemy + row0, count, e->dp.policy + row0 * 64,
-                                                          e->dp.value + row0);
-            RZ_LAUNCH_CHECK();
-            e->mcts_launches++;
-        } else {
-            RZ_TRY(net_forward_counted(e->net, e->dp.batch_own + row0, e->dp.batch_enemy + row0, e->dp.policy + row0 * 64, e->dp.value + row0,
-                                       count, rows, e->cfg.net_impl, st));
-            e->nn_launches++;
+        for (int net = 0; net <= c.two_nets; ++net) {
+            uint32_t* count = e->dp.batch_count + (net * 2 + g) * 64;
+            const size_t row0 = (size_t)net * c.G * c.K + (size_t)s0 * c.K;
+            if (e->cfg.eval_mode == RZ_EVAL_FAKE) {
+                fake_eval_kernel<<<num_sms() * 4, 256, 0, st>>>(e->dp.batch_own + row0, e->dp.batch_enemy + row0, count, e->dp.policy + row0 * 64,
+                                                              e->dp.value + row0, net ? -1.f : 1.f);
+                RZ_LAUNCH_CHECK();
+                e->mcts_launches++;
+            } else {
+                RZ_TRY(net_forward_counted(net ? e->net_b : e->net, e->dp.batch_own + row0, e->dp.batch_enemy + row0, e->dp.policy + row0 * 64,
+                                           e->dp.value + row0, count, rows, e->cfg.net_impl, st));
+                e->nn_launches++;
+            }
         }
         if (timed) RZ_CUDA_TRY(cudaEventRecord(ev[2], st));
     }
@@ -797,7 +807,7 @@ int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net, int device, rz_engin
     RZ_CUDA_TRY(cudaSetDevice(device));
     rz_engine* e = new (std::nothrow) rz_engine();
     if (!e) { set_error("out of host memory"); return RZ_ENOMEM; }
-    e->cfg = *cfg; e->net = net; e->device = device; e->n_arena = 0;
+    e->cfg = *cfg; e->net = net; e->net_b = nullptr; e->device = device; e->n_arena = 0;
     e->waves = e->nn_launches = e->mcts_launches = e->finished_total = 0;
     e->h_status = nullptr; e->h_flags = nullptr; e->stream = nullptr; e->stream2 = nullptr;
     e->ev_used = 0; e->nn_ms = e->mcts_ms = e->run_ms = 0.0;
@@ -817,6 +827,7 @@ int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net, int device, rz_engin
     c.start_rethinking_turn = cfg->start_rethinking_turn; c.allowed_resign_turn = cfg->allowed_resign_turn;
     c.use_resign = cfg->use_resign_threshold; c.share = cfg->share_mtcs_info; c.max_plies = cfg->max_plies > 0 ? cfg->max_plies : 64;
     c.warm_start = cfg->warm_start;
+    c.two_nets = 0;
     c.sims_cap = cfg->max_sims_per_wave > 0 ? cfg->max_sims_per_wave : 2 * cfg->parallel_search_num;
     c.c_puct = cfg->c_puct; c.noise_eps = cfg->noise_eps; c.alpha = cfg->dirichlet_alpha; c.resign_threshold = cfg->resign_threshold;
     c.disable_resignation_rate = cfg->disable_resignation_rate;
@@ -835,10 +846,10 @@ int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net, int device, rz_engin
     cudaError_t ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking);
     if (ce != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(ce)); delete e; return RZ_ECUDA; }
-    const size_t G = c.G, B = G * c.K;
+    const size_t G = c.G, B = 2 * G * c.K;  // rows for two networks (evaluation matches); self-play uses the first half
     DevPtrs& p = e->dp;
     rc = dev_alloc(e, (void**)&p.slots, G * sizeof(Slot), true);
-    if (!rc) rc = dev_alloc(e, (void**)&p.desc, B * sizeof(Descent), true);
+    if (!rc) rc = dev_alloc(e, (void**)&p.desc, G * c.K * sizeof(Descent), true);
     if (!rc) rc = dev_alloc(e, (void**)&p.hash, G * c.hash_cap * sizeof(uint32_t), true);
     if (!rc) rc = dev_alloc(e, (void**)&p.nodes, G * c.nodes_cap * sizeof(Node), false);
     if (!rc) rc = dev_alloc(e, (void**)&p.edges, G * (size_t)c.edges_cap * sizeof(Edge), false);
@@ -957,6 +968,15 @@ int rz_engine_set_simulation_num(rz_engine* e, int32_t sims) {
     RZ_REQUIRE(need <= e->dc.nodes_cap, "simulation count %d exceeds the arenas sized at creation", sims);
     e->dc.S = sims;
     e->cfg.simulation_num_per_move = sims;
+    return RZ_OK;
+}
+
+int rz_engine_set_second_net(rz_engine* e, rz_net* net_b, int enable) {
+    RZ_REQUIRE(e, "rz_engine_set_second_net: null engine");
+    RZ_REQUIRE(!enable || e->cfg.eval_mode == RZ_EVAL_FAKE || net_b, "rz_engine_set_second_net: a second network is required");
+    RZ_REQUIRE(e->waves == 0, "rz_engine_set_second_net: must be called before the first wave");
+    e->net_b = enable ? net_b : nullptr;
+    e->dc.two_nets = enable ? 1 : 0;
     return RZ_OK;
 }
 

@@ -313,6 +313,7 @@ struct WCtx {
 
     __device__ void begin_search(u64 own, u64 enemy, int pid) {
         sl.root_own = own; sl.root_enemy = enemy; sl.root_pid = (uint8_t)pid;
+        sl.cur_net = c.two_nets ? (uint8_t)(pid == 1 ? sl.black_net : 1 - sl.black_net) : (uint8_t)0;
         sl.sims_started = 0; sl.sims_target = (uint32_t)c.S;
         sl.n_pending = 0; sl.n_parked = 0;
         sl.phase = PH_SEARCH;
@@ -326,6 +327,7 @@ struct WCtx {
             return;
         }
         sl.game_id = c.first_game_id + local * c.game_id_stride;
+        sl.black_net = c.two_nets ? (uint8_t)(local & 1) : (uint8_t)0;
         sl.games_played++;
         env_reset(sl.env);
         sl.gen = sl.gen + 1;
@@ -364,6 +366,7 @@ struct WCtx {
             g.first_ply = 0; g.n_plies = (int32_t)sl.ply; g.expansions = (int32_t)sl.n_expand; g.simulations = (int32_t)sl.n_sims;
             g.winner = sl.env.winner; g.black_z = sl.env.winner == 1 ? 1 : (sl.env.winner == 2 ? -1 : 0);
             g.resign_enabled = sl.enable_resign; g.resigned_mask = sl.resigned_mask; g.turn = sl.env.turn;
+            g.black_net = sl.black_net; g.pad[0] = g.pad[1] = 0;
             atomicMax(&p.status->max_nodes, (unsigned long long)sl.n_nodes);
             atomicMax(&p.status->max_edges, (unsigned long long)sl.n_edges);
             __threadfence();
@@ -502,11 +505,12 @@ __global__ void __launch_bounds__(kWarpTickThreads) tick_warp_kernel(const DevCf
     x.write_back();
     // 3. gather (K3): one atomic per game, the lanes write the dihedral-transformed leaves of this game
     uint32_t base = 0;
-    if (lane == 0 && n_leaves > 0) base = atomicAdd(p.batch_count + group * 64, (uint32_t)n_leaves);
+    const uint32_t net = c.two_nets ? sl.cur_net : 0u;  // evaluation matches: every search is evaluated by the mover's network
+    if (lane == 0 && n_leaves > 0) base = atomicAdd(p.batch_count + (net * 2 + group) * 64, (uint32_t)n_leaves);
     base = __shfl_sync(0xffffffffu, base, 0);
     if (lane < n_leaves) {
         Descent& d = x.desc[sl.pending[lane]];
-        const uint32_t at = (uint32_t)slot0 * (uint32_t)c.K + base + (uint32_t)lane;
+        const uint32_t at = net * (uint32_t)c.G * (uint32_t)c.K + (uint32_t)slot0 * (uint32_t)c.K + base + (uint32_t)lane;
         d.leaf_index = at;
         p.batch_own[at] = dihedral(d.leaf_own, d.dihedral);
         p.batch_enemy[at] = dihedral(d.leaf_enemy, d.dihedral);

@@ -46,7 +46,7 @@ class Game(C.Structure):
     _fields_ = [("game_id", C.c_uint64), ("black", C.c_uint64), ("white", C.c_uint64), ("first_ply", C.c_int32),
                 ("n_plies", C.c_int32), ("expansions", C.c_int32), ("simulations", C.c_int32), ("winner", C.c_uint8),
                 ("black_z", C.c_int8), ("resign_enabled", C.c_uint8), ("resigned_mask", C.c_uint8), ("turn", C.c_uint8),
-                ("pad", C.c_uint8 * 3)]
+                ("black_net", C.c_uint8), ("pad", C.c_uint8 * 2)]
 
 
 class Stats(C.Structure):
@@ -87,6 +87,7 @@ SIGNATURES = {
     "rz_engine_poll": (C.c_int, [vp, C.POINTER(Game), sz, C.POINTER(sz), C.POINTER(Ply), sz, C.POINTER(sz)]),
     "rz_engine_stats": (C.c_int, [vp, C.POINTER(Stats)]),
     "rz_engine_set_simulation_num": (C.c_int, [vp, C.c_int32]),
+    "rz_engine_set_second_net": (C.c_int, [vp, vp, C.c_int]),
     "rz_engine_set_resign_threshold": (C.c_int, [vp, C.c_int, C.c_float]),
     "rz_engine_search_root": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, i32p, f32p]),
     "rz_write_play_data": (C.c_int, [C.c_char_p, C.POINTER(Game), sz, C.POINTER(Ply), C.c_int, C.c_int, C.POINTER(sz)]),

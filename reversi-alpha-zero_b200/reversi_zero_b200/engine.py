@@ -81,7 +81,8 @@ class Engine:
                                    pid=int(p.player), loops=int(p.loops), recorded=bool(p.recorded), n=float(p.n), q=float(p.q)))
                 out.append(dict(game_id=int(g.game_id), black=int(g.black), white=int(g.white), winner=int(g.winner),
                                 black_z=int(g.black_z), expansions=int(g.expansions), simulations=int(g.simulations),
-                                resign_enabled=bool(g.resign_enabled), resigned_mask=int(g.resigned_mask), turn=int(g.turn), plies=pl))
+                                resign_enabled=bool(g.resign_enabled), resigned_mask=int(g.resigned_mask), turn=int(g.turn),
+                                black_net=int(g.black_net), plies=pl))
         return out
 
     def stats(self):
@@ -91,6 +92,12 @@ class Engine:
 
     def set_simulation_num(self, sims):
         _cabi.check(_cabi.lib().rz_engine_set_simulation_num(self._h, int(sims)), "rz_engine_set_simulation_num")
+
+    def set_second_net(self, net_b=None, enable=True):
+        """evaluation matches: even local game indices -> first network plays black, odd -> second network."""
+        self.net_b = net_b  # keep alive
+        _cabi.check(_cabi.lib().rz_engine_set_second_net(self._h, net_b.handle if net_b is not None else None, int(bool(enable))),
+                    "rz_engine_set_second_net")
 
     def set_resign_threshold(self, threshold):
         _cabi.check(_cabi.lib().rz_engine_set_resign_threshold(self._h, 0 if threshold is None else 1,

@@ -1,0 +1,120 @@
+"""Mirror of the reference's evaluator (worker/evaluate.py:17-124) on the B200 engine: the challenger
+("next generation") network plays ``eval.game_num`` games against the best network and replaces it when its
+winning rate over the decided games reaches ``eval.replace_rate``.
+
+The reference plays the games one after the other with two in-process ``ReversiPlayer`` objects; here ALL games of
+a match run concurrently on the device (``rz_engine_set_second_net``): each search is evaluated by the mover's own
+network, colours alternate by game index (the reference draws them at random, :70), each player keeps its own
+statistics (``share_mtcs_info = 0``, as ``ReversiPlayer(config, model, play_config=...)`` does in :69-70).  The
+early-stop rules (:56-61) only shorten a sequential match; with concurrent games the verdict is computed from all
+finished games.  Weights are exchanged as float32 blobs (``*.rzblob.npy``)."""
+import os
+import shutil
+from glob import glob
+from logging import getLogger
+from time import sleep
+from types import SimpleNamespace
+
+import numpy as np
+
+from ..engine import Engine, engine_cfg_from_play_config, EVAL_NET
+from ..net import Net
+from .self_play import blob_path_of
+
+logger = getLogger(__name__)
+
+NEXT_GENERATION_BLOB = "model_weight.rzblob.npy"
+
+
+def start(config):
+    return EvaluateWorker(config).start()
+
+
+def eval_play_config(config):
+    """EvaluateConfig.play_config defaults (config.py:103-113) over the self-play PlayConfig, or the
+    ``eval.play_config`` mapping of a YAML file."""
+    pc = SimpleNamespace(**vars(config.play))
+    over = dict(simulation_num_per_move=400, thinking_loop=1, change_tau_turn=0, noise_eps=0, disable_resignation_rate=0)
+    ev = getattr(config, "eval", None)
+    user = (ev.get("play_config") if isinstance(ev, dict) else getattr(ev, "play_config", None)) or {}
+    over.update(user if isinstance(user, dict) else vars(user))
+    for k, v in over.items():
+        setattr(pc, k, v)
+    pc.share_mtcs_info_in_self_play = False
+    return pc
+
+
+def _eval_field(config, name, default):
+    ev = getattr(config, "eval", None)
+    if isinstance(ev, dict):
+        return ev.get(name, default)
+    return getattr(ev, name, default) if ev is not None else default
+
+
+def play_match(config, best_net, ng_net, game_num, device=0, seed=0):
+    """-> (results, games): results[i] = 1 challenger won, 0 lost, None draw (worker/evaluate.py:84-96)."""
+    pc = eval_play_config(config)
+    slots = min(game_num, getattr(getattr(config, "b200", None), "games_per_gpu", 4096))
+    cfg = engine_cfg_from_play_config(pc, games=slots, seed=seed, eval_mode=EVAL_NET, max_games=game_num)
+    eng = Engine(cfg, best_net, device)
+    eng.set_second_net(ng_net)
+    eng.run(finished_target=game_num)
+    games = sorted(eng.poll(), key=lambda g: g["game_id"])
+    eng.close()
+    results = []
+    for g in games:
+        best_is_black = g["black_net"] == 0
+        if g["winner"] == 1:
+            results.append(0 if best_is_black else 1)
+        elif g["winner"] == 2:
+            results.append(1 if best_is_black else 0)
+        else:
+            results.append(None)
+    return results, games
+
+
+class EvaluateWorker:
+    def __init__(self, config, device=0):
+        self.config = config
+        self.device = device
+        self.best_net = None
+
+    def start(self, max_models=None):
+        self.best_net = self._load(blob_path_of(self.config))
+        done = 0
+        while max_models is None or done < max_models:
+            model_dir = self.next_generation_dir()
+            ng_net = self._load(os.path.join(model_dir, NEXT_GENERATION_BLOB))
+            logger.debug(f"start evaluate model {model_dir}")
+            if self.evaluate_model(ng_net):
+                logger.debug(f"New Model become best model: {model_dir}")
+                shutil.copyfile(os.path.join(model_dir, NEXT_GENERATION_BLOB), blob_path_of(self.config))  # save_as_best_model
+                self.best_net = ng_net
+            shutil.rmtree(model_dir, ignore_errors=True)                                                  # remove_model, :115-121
+            done += 1
+        return done
+
+    def evaluate_model(self, ng_net):
+        """worker/evaluate.py:44-64"""
+        game_num = int(_eval_field(self.config, "game_num", 200))
+        replace_rate = float(_eval_field(self.config, "replace_rate", 0.55))
+        results, _ = play_match(self.config, self.best_net, ng_net, game_num, self.device)
+        decided = [r for r in results if r is not None]
+        winning_rate = sum(decided) / len(decided) if decided else 0.0
+        logger.debug(f"winning rate {winning_rate * 100:.1f}% over {len(decided)} decided games")
+        return winning_rate >= replace_rate
+
+    def next_generation_dir(self):
+        rc = self.config.resource
+        while True:
+            dirs = sorted(glob(os.path.join(rc.next_generation_model_dir, rc.next_generation_model_dirname_tmpl % "*")))
+            dirs = [d for d in dirs if os.path.exists(os.path.join(d, NEXT_GENERATION_BLOB))]
+            if dirs:
+                return dirs[-1] if _eval_field(self.config, "evaluate_latest_first", True) else dirs[0]
+            logger.info("There is no next generation model to evaluate")
+            sleep(60)
+
+    def _load(self, path):
+        net = Net(self.config.model, self.device)
+        net.load_blob(np.load(path))
+        return net

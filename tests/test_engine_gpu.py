@@ -172,3 +172,50 @@ def test_search_with_real_network_matches_oracle():
     assert max(dist) <= 12, dist
     eng.close()
     net.close()
+
+
+def test_evaluation_match_two_networks_exact():
+    """rz_engine_set_second_net (worker/evaluate.py:66-96): each search is evaluated by the mover's own network and the
+    colours alternate with the game index.  Deterministic evaluators (the second one negates the value): whole games
+    must equal the oracle driven with the same two evaluators."""
+    pp = params(simulation_num_per_move=30, share_mtcs_info_in_self_play=False, change_tau_turn=0)
+    eng = make_engine(pp, games=3, seed=41, max_games=6)
+    eng.set_second_net(None, enable=True)
+    eng.run(finished_target=6)
+    games = sorted(eng.poll(), key=lambda g: g["game_id"])
+    eng.close()
+    assert [g["black_net"] for g in games] == [0, 1, 0, 1, 0, 1]
+    for g in games:
+        replay_check(g)
+        o = mcts.SelfPlayGame(pp, onn.FakeNetAPI(), seed=41, game_id=g["game_id"], api_b=onn.FakeNetAPI(sign=-1.0),
+                              black_net=g["black_net"]).play()
+        assert [(p["own"], p["enemy"], p["action"], list(p["N"])) for p in g["plies"]] == \
+               [(p["own"], p["enemy"], p["action"], list(p["N"])) for p in o.plies]
+        assert g["winner"] == o.env.winner
+    # the two evaluators really differ: the match is not symmetric
+    assert len({(g["winner"], g["black_net"]) for g in games}) > 1 or len({g["black"] for g in games}) > 1
+
+
+def test_evaluate_worker_with_real_networks(tmp_path):
+    """EvaluateWorker mirror: identical weights -> a balanced match that does not promote the challenger at 0.9;
+    files (best blob, next_generation dir) handled like worker/evaluate.py:33-43,115-121."""
+    from reversi_zero_b200.config import Config
+    from reversi_zero_b200.agent import model as M
+    from reversi_zero_b200.worker import evaluate as EV
+    cfg = Config(project_dir=str(tmp_path), data_dir=str(tmp_path / "data"))
+    cfg.model.update(dict(cnn_filter_num=16, res_layer_num=1, value_fc_size=16))
+    cfg.play.update(dict(c_puct=5, parallel_search_num=4))
+    cfg.eval = dict(game_num=12, replace_rate=0.9, play_config=dict(simulation_num_per_move=16, c_puct=1))
+    cfg.resource.create_directories()
+    blob = M.weights_to_blob(cfg.model, M.build_random_weights(cfg.model, 1))
+    np.save(cfg.resource.model_best_blob_path, blob)
+    ng_dir = os.path.join(cfg.resource.next_generation_model_dir, cfg.resource.next_generation_model_dirname_tmpl % "20260922-000000.000000")
+    os.makedirs(ng_dir)
+    np.save(os.path.join(ng_dir, EV.NEXT_GENERATION_BLOB), blob)
+    w = EV.EvaluateWorker(cfg)
+    w.best_net = w._load(cfg.resource.model_best_blob_path)
+    results, games = EV.play_match(cfg, w.best_net, w._load(os.path.join(ng_dir, EV.NEXT_GENERATION_BLOB)), 12)
+    assert len(results) == 12 and all(r in (0, 1, None) for r in results)
+    for g in games:
+        replay_check(g)
+    assert w.start(max_models=1) == 1 and not os.path.exists(ng_dir)      # evaluated, not promoted, directory removed
