@@ -98,6 +98,7 @@ class B200Config(_Section):
         self.seed = 20260922
         self.net_impl = 0           # RZ_NET_IMPL_AUTO
         self.weight_seed = 0        # random-init seed used when no weights exist (`--new`, agent/api.py:112-114)
+        self.tensorboard = False    # write self/time, self/turn scalars like worker/self_play.py:125-129
 
 
 class Config(_Section):

@@ -97,6 +97,7 @@ class SelfPlayWorker:
         self.game_idx = 0
         self.files_written = []
         self.last_model_check_time = time.time()
+        self.tensor_board = None
 
     # -- reference helpers ---------------------------------------------------------------------------------
     def decide_simulation_num_per_move(self, idx):
@@ -201,9 +202,24 @@ class SelfPlayWorker:
         self._flush_files(force=True)
         return finished
 
+    def _log_scalars(self, g, n_plies, seconds_per_game):
+        """worker/self_play.py:125-129: self/time, self/turn (+ engine counters) under logs/tensorboard/self_play/workerNNN"""
+        if self.tensor_board is None:
+            try:
+                from torch.utils.tensorboard import SummaryWriter
+                self.tensor_board = SummaryWriter(os.path.join(self.config.resource.self_play_log_dir, f"worker{self.rank:03d}"))
+            except Exception:  # tensorboard not installed: scalars are optional
+                self.tensor_board = False
+        if self.tensor_board:
+            self.tensor_board.add_scalar("self/time", seconds_per_game, self.game_idx)
+            self.tensor_board.add_scalar("self/turn", int(g.turn), self.game_idx)
+            self.tensor_board.add_scalar("self/expansions", int(g.expansions), self.game_idx)
+
     def _harvest(self):
         n_total = 0
         pdc, pc = self.config.play_data, self.config.play
+        now = time.time()
+        elapsed, self._last_harvest_time = now - getattr(self, "_last_harvest_time", now), now
         while True:
             games, ng, plies, _ = self.engine.poll_raw()
             if ng == 0:
@@ -215,6 +231,8 @@ class SelfPlayWorker:
                 self.game_idx += self.world_size
                 gp = [plies[j] for j in range(g.first_ply, g.first_ply + g.n_plies)]
                 self._finish_game(g)
+                if getattr(self.config.b200 if hasattr(self.config, "b200") else None, "tensorboard", False):
+                    self._log_scalars(g, len(gp), elapsed / max(1, ng))
                 # drop draw games with probability drop_draw_game_rate (self_play.py:182)
                 if g.black_z != 0 or pdc.drop_draw_game_rate <= np.random.random():
                     self.buffer_games.append((_copy(g), [_copy(p) for p in gp]))
