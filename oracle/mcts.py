@@ -26,6 +26,7 @@ import numpy as np
 
 from . import bitboard as bb
 from . import philox as px
+from .solver import Solver
 
 f32, f64 = np.float32, np.float64
 
@@ -49,6 +50,8 @@ class PlayParams:
         self.disable_resignation_rate = 0.1
         self.share_mtcs_info_in_self_play = True
         self.save_policy_of_tau_1 = True
+        self.use_solver_turn = 0                # config.py:154; 0 = solver off (agent/player.py:100)
+        self.use_solver_turn_in_simulation = 0  # config.py:155 (agent/player.py:237-238)
         self.max_sims_per_wave = 0  # engine knob (0 = 2 * parallel_search_num): simulations started per game per wave
         for k, v in kw.items():
             if not hasattr(self, k):
@@ -57,7 +60,7 @@ class PlayParams:
 
 
 class Node:
-    __slots__ = ("legal", "legal_arr", "P", "pn", "N", "W", "exp")
+    __slots__ = ("legal", "legal_arr", "P", "pn", "N", "W", "exp", "wld")
 
     def __init__(self, legal):
         self.legal = legal
@@ -66,6 +69,7 @@ class Node:
         self.pn = np.zeros(64, f32)
         self.N = np.zeros(64, np.int64)
         self.W = np.zeros(64, f32)
+        self.wld = None  # cached (action, score) of the in-simulation WLD solve of this position
         self.exp = 0  # bit (pid-1) set once player pid expanded it (each ReversiPlayer has its own
         #               `expanded` set even when N/W/P dicts are shared, player.py:44-47)
 
@@ -148,6 +152,9 @@ class SelfPlayGame:
         self.n_waves = 0
         self.plies = []        # dicts: pid, own, enemy, N, policy, saved_policy, action, n, q, loops
         self.resigned = {1: False, 2: False}
+        self.solver = {1: Solver(), 2: Solver()}  # one ReversiSolver per ReversiPlayer (player.py:60,435-436)
+        self.n_solves = 0
+        self.solved_plies = []
         self.enable_resign = pp.disable_resignation_rate <= px.u01(px.draw(seed, game_id, 0, px.P_GAME)[0])
 
     # -- keys ------------------------------------------------------------------------------------
@@ -174,6 +181,17 @@ class SelfPlayGame:
                 return "done"
             own, enemy = e.own_enemy()
             key = self._key(own, enemy, pid)
+            if pp.use_solver_turn_in_simulation and e.turn >= pp.use_solver_turn_in_simulation:  # player.py:237-251
+                node = self.table.get(key)
+                if node is not None and node.wld is not None:
+                    if self._apply_wld(d, node, e.next_player == pid):
+                        return "done"
+                elif key in pending_keys:
+                    return "parked"
+                else:  # the engine solves on the device between two waves: request, like a network evaluation
+                    pending_keys.add(key)
+                    pending.append((d, key, own, enemy, -1, e.next_player == pid))
+                    return "pending"
             if key in pending_keys:  # player.py:253-254
                 return "parked"
             node = self.table.get(key)
@@ -195,6 +213,21 @@ class SelfPlayGame:
             node.W[a] = f32(node.W[a] - f32(vl))
             d.path.append((node, a, e.next_player == pid))
             e.step(a)
+
+    def _apply_wld(self, d, node, mover_is_root):
+        """player.py:239-251 with the cached result (action, score) of the WLD solve; returns False when the reference's
+        `if action:` test fails (no result, or the solved move is square 0)."""
+        action, score = node.wld
+        if not action:
+            return False
+        sgn = f32(np.sign(score))                      # value for the side to move at this node
+        node.N[action] += 1
+        node.W[action] = f32(node.W[action] + sgn)
+        node.P = np.zeros(64, f32)
+        node.P[action] = 1
+        node.pn = node.P.copy()
+        self._backup(d.path, float(sgn) if mover_is_root else -float(sgn))
+        return True
 
     def _backup(self, path, v_root):
         """player.py:276-280."""
@@ -230,30 +263,45 @@ class SelfPlayGame:
                     break
                 continue
             self.n_waves += 1
-            self._evaluate(pending, pid)
+            parked = parked + self._evaluate(pending, pid)
             if self.deadline is not None and time.perf_counter() > self.deadline:
                 self.n_sims += started
                 raise TimeUp()
         self.n_sims += started
 
     def _evaluate(self, pending, pid):
-        """player.py:283-327 for a whole wave."""
-        t_own = np.array([bb.dihedral(o, t) for (_, _, o, e, t, _) in pending], dtype=np.uint64)
-        t_en = np.array([bb.dihedral(e, t) for (_, _, o, e, t, _) in pending], dtype=np.uint64)
-        sh = np.arange(64, dtype=np.uint64)
-        planes = np.stack([((t_own[:, None] >> sh) & np.uint64(1)), ((t_en[:, None] >> sh) & np.uint64(1))],
-                          axis=1).astype(np.uint8).reshape(-1, 2, 8, 8)
-        net = 0 if self.api_b is None else (self.black_net if pid == 1 else 1 - self.black_net)
-        policy, value = (self.api_b if net else self.api).predict(planes)
-        for i, (d, key, own, enemy, t, mover_is_root) in enumerate(pending):
+        """player.py:283-327 for a whole wave (network requests) + the WLD solves requested in this wave; results are
+        consumed in request order."""
+        nn = [x for x in pending if x[4] >= 0]
+        policy = value = None
+        resume = []
+        if nn:
+            t_own = np.array([bb.dihedral(o, t) for (_, _, o, e, t, _) in nn], dtype=np.uint64)
+            t_en = np.array([bb.dihedral(e, t) for (_, _, o, e, t, _) in nn], dtype=np.uint64)
+            sh = np.arange(64, dtype=np.uint64)
+            planes = np.stack([((t_own[:, None] >> sh) & np.uint64(1)), ((t_en[:, None] >> sh) & np.uint64(1))],
+                              axis=1).astype(np.uint8).reshape(-1, 2, 8, 8)
+            net = 0 if self.api_b is None else (self.black_net if pid == 1 else 1 - self.black_net)
+            policy, value = (self.api_b if net else self.api).predict(planes)
+        i = 0
+        for (d, key, own, enemy, t, mover_is_root) in pending:
             node = self.table.get(key)
             if node is None:
                 node = self.table[key] = Node(bb.find_correct_moves(own, enemy))
+            if t < 0:  # WLD solve (player.py:239)
+                self.n_solves += 1
+                mv, sc = self.solver[pid].solve(own, enemy, exactly=False)
+                node.wld = (mv, sc)
+                if not self._apply_wld(d, node, mover_is_root):
+                    resume.append(d)  # `if action:` failed: the simulation goes on from this node in the next wave
+                continue
             node.P = inverse_policy(np.asarray(policy[i], f32), t).astype(f32)
             node.pn = normalize_prior(node.P, node.legal_arr)
             node.exp |= 1 << (pid - 1)
             v = float(np.asarray(value[i]).reshape(-1)[0])
+            i += 1
             self._backup(d.path, v if mover_is_root else -v)
+        return resume
 
     # -- per-ply decision ---------------------------------------------------------------------------
     def decide(self, own, enemy, pid):
@@ -263,6 +311,20 @@ class SelfPlayGame:
         key = self._key(own, enemy, pid)
         ply = len(self.plies)
         loops = 0
+        if pp.use_solver_turn and turn >= pp.use_solver_turn:  # action_by_searching, player.py:100-103,150-161
+            mv, sc = self.solver[pid].solve(own, enemy, exactly=True)
+            if mv is not None:
+                root = self.table.get(key)
+                if root is None:
+                    root = self.table[key] = Node(bb.find_correct_moves(own, enemy))
+                sgn = float(np.sign(sc))
+                root.N[mv] = 999
+                root.W[mv] = f32(sgn * 999)
+                root.P = np.zeros(64, f32)
+                root.P[mv] = 1
+                root.pn = root.P.copy()
+                self.solved_plies.append(dict(pid=pid, own=own, enemy=enemy, action=mv, n=999.0, q=sgn, turn=turn))
+                return mv  # not saved as play data (player.py:102)
         for tl in range(pp.thinking_loop):
             loops += 1
             if turn > 0:

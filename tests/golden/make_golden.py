@@ -246,7 +246,58 @@ def gen_mcts():
     return out
 
 
+def gen_solver():
+    """lib/alt/reversi_solver (Cython, what agent/player.py:15 imports): KATs of lib/reversi_solver.py:102-154 and
+    random endgame positions, exact and WLD, a fresh solver per call."""
+    from reversi_zero.lib.alt.reversi_solver import ReversiSolver
+    rng = np.random.default_rng(SEED + 3)
+    out = []
+    kat = [("q1", 0x80feafd2eaf20200, 0x7c00502d150d0d0f, 2, False), ("q2", 0xfffeadd0c0c00000, 0x0000522f3f3f2f0f, 1, False),
+           ("q3", 0x3c1e8e9e9ad0a870, 0x40607161652f1504, 2, True)]
+    for name, b, w, pl, exact in kat:
+        mv, sc = ReversiSolver().solve(b, w, Player(pl), exactly=exact)
+        out.append(dict(tag=name, black=b, white=w, next_player=pl, exactly=exact, move=int(mv), score=int(sc)))
+    n = 0
+    while n < 120:
+        empties = int(rng.integers(1, 10))
+        env = ReversiEnv().reset()
+        while not env.done and 60 - env.turn > empties:
+            o, e = env.get_own_and_enemy()
+            legal = rb.find_correct_moves(o, e)
+            ms = [i for i in range(64) if legal >> i & 1]
+            env.step(int(ms[rng.integers(len(ms))]))
+        if env.done:
+            continue
+        for exact in (True, False):
+            mv, sc = ReversiSolver().solve(env.board.black, env.board.white, env.next_player, exactly=exact)
+            out.append(dict(tag=f"rand{n}", black=int(env.board.black), white=int(env.board.white), next_player=env.next_player.value,
+                            exactly=exact, move=int(mv), score=int(sc)))
+        n += 1
+    return out
+
+
+def gen_mcts_solver():
+    """whole games of the reference player with the solver hooks on (agent/player.py:100-103,237-251), K = 1, tau = 0"""
+    out = {}
+    for name, sims, ust, usim in (("solver_s16_t52", 16, 52, 52), ("solver_s12_t50_sim54", 12, 50, 54), ("solver_s40_t56_sim51", 40, 56, 51)):
+        api = FakeNet()
+        cfg = ref_config(sims=sims, k=1, noise_eps=0, change_tau_turn=0, share=True)
+        cfg.play.use_solver_turn = ust
+        cfg.play.use_solver_turn_in_simulation = usim
+        plies, recs, z = ref_selfplay_game(cfg, api)
+        import hashlib
+        out[name] = dict(sims=sims, use_solver_turn=ust, use_solver_turn_in_simulation=usim, c_puct=5, plies=plies, z=z, n_records=len(recs),
+                         records_sha256=hashlib.sha256(json.dumps(recs).encode()).hexdigest(), expansions=api.rows)
+    return out
+
+
 def main():
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "solver":   # only (re)generate the solver fixtures
+        with open(os.path.join(HERE, "solver.json"), "w") as f:
+            json.dump(dict(positions=gen_solver(), mcts=gen_mcts_solver()), f)
+        print("solver golden vectors written")
+        return
     kats = gen_bitboard()
     env = gen_env()
     sym = gen_symmetry()

@@ -144,3 +144,37 @@ def test_oracle_nn_shapes():
     p, v = nn.forward(w, planes, 1)
     assert p.shape == (2, 64) and v.shape == (2,) and np.allclose(p.sum(1), 1, atol=1e-5)
     assert planes[0, 0, 3, 4] == 1 and planes[0, 1, 3, 3] == 1  # bit 28 = (y=3,x=4)
+
+
+def test_solver_vs_reference(golden_dir):
+    """oracle/solver.py against the reference's Cython solver (lib/alt/reversi_solver_cython.pyx): the KATs of
+    lib/reversi_solver.py:102-154 (q1 -> (57, +2), q2 -> (4|14, -2), q3 -> (3, +2)) and 120 random endgames, exact + WLD."""
+    from oracle.solver import Solver
+    g = _load(golden_dir, "solver.json")
+    kat = {c["tag"]: c for c in g["positions"] if c["tag"].startswith("q")}
+    assert (kat["q1"]["move"], kat["q1"]["score"]) == (57, 2) and kat["q2"]["score"] == -2 and kat["q2"]["move"] in (4, 14)
+    assert (kat["q3"]["move"], kat["q3"]["score"]) == (3, 2)
+    for c in g["positions"]:
+        own, enemy = (c["black"], c["white"]) if c["next_player"] == 1 else (c["white"], c["black"])
+        assert Solver().solve(own, enemy, c["exactly"]) == (c["move"], c["score"]), c["tag"]
+
+
+def test_mcts_with_solver_exact_vs_reference(golden_dir):
+    """whole games with the solver hooks on (agent/player.py:100-103,237-251), K = 1: every ply (searched or solved),
+    root visit counts, training records and the number of network evaluations equal the reference's."""
+    g = _load(golden_dir, "solver.json")["mcts"]
+    for name, ref in g.items():
+        pp = mcts.PlayParams(simulation_num_per_move=ref["sims"], parallel_search_num=1, noise_eps=0.0, change_tau_turn=0, c_puct=5,
+                             thinking_loop=1, resign_threshold=None, use_solver_turn=ref["use_solver_turn"],
+                             use_solver_turn_in_simulation=ref["use_solver_turn_in_simulation"])
+        game = mcts.SelfPlayGame(pp, nn.FakeNetAPI(), seed=7, game_id=0).play()
+        mine = sorted(game.plies + game.solved_plies, key=lambda r: r["turn"])
+        assert len(mine) == len(ref["plies"]), name
+        for a, b in zip(mine, ref["plies"]):
+            assert (a["pid"], a["own"], a["enemy"], a["action"]) == (b["pid"], b["own"], b["enemy"], b["action"]), (name, a["turn"])
+            if "N" in a:
+                assert list(a["N"]) == b["N"], (name, a["turn"])
+            assert abs(a["q"] - b["q"]) < 1e-6 and a["n"] == b["n"]
+        recs = [[[int(o), int(e)], [float(x) for x in p], int(z)] for (o, e), p, z in game.records()]
+        assert hashlib.sha256(json.dumps(recs).encode()).hexdigest() == ref["records_sha256"], name
+        assert game.n_expand == ref["expansions"] and game.black_z == ref["z"]
