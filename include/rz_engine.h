@@ -70,6 +70,16 @@ int rz_step(uint64_t* black, uint64_t* white, uint8_t* next_player, uint8_t* tur
  * of agent/player.py:166-179 and :300-305.  Replaces lib/bitboard.py:119-159. */
 int rz_dihedral_dev(const uint64_t* x, const uint8_t* t, uint64_t* out, size_t n, void* stream);
 
+/* endgame solver (lib/alt/reversi_solver_cython.pyx:40-127 ReversiSolver.solve, the variant agent/player.py:15
+ * imports), batched: for each position of the side to move, move[i] = best square and score[i] = its value in the
+ * mover's frame.  exactly[i] != 0: exact final disc difference, first best move in ascending order; exactly[i] == 0:
+ * win/loss/draw mode with the reference's early stop (only the sign of the score and the move are meaningful).
+ * move[i] = -1 (score 0): no legal move, or more than 12 empty squares (the analogue of the reference's timeout,
+ * after which ReversiPlayer falls back to the search). */
+int rz_solve_dev(const uint64_t* own, const uint64_t* enemy, const uint8_t* exactly, int8_t* move, int8_t* score, size_t n,
+                 void* stream);
+int rz_solve(const uint64_t* own, const uint64_t* enemy, const uint8_t* exactly, int8_t* move, int8_t* score, size_t n);
+
 /* Scalar host twins for the single-environment Python objects (ReversiEnv / Board used by the
  * reference's evaluate.py, nboard.py, game_model.py): same header-only code as the device kernels
  * (csrc/rz_bitboard.cuh), compiled for the host.  Not a fallback for the batched path. */

@@ -1,0 +1,127 @@
+// rz_solver.cuh -- endgame solver on the device (lib/alt/reversi_solver_cython.pyx:63-127, the variant agent/player.py:15
+// imports): result (move, score) of a position for the side to move, identical to the reference's
+//   * exactly = 1: best final disc difference, FIRST move (ascending square) that reaches it (strict '<' at :92-95);
+//   * exactly = 0 (win/loss/draw): plain minimax in which every node stops at its first move with a positive score (:99);
+//     the returned score is that early-stopped score, so only its sign and the chosen move are meaningful.
+// One WARP solves one position: the two top plies are enumerated, every grand-child position becomes a task, the lanes
+// solve the tasks independently (iterative negamax on a private stack; alpha-beta in exact mode -- inner nodes only need
+// their value, which pruning does not change; the literal early-stop recursion in WLD mode), and the top two plies are
+// then combined sequentially in the reference's move order, so ties and early stops resolve exactly as in the reference.
+// Positions with more than kSolverMaxEmpties empty squares are refused (move = -1), the analogue of the reference's
+// 30-second timeout (:78-79) after which the player falls back to the search.
+#pragma once
+#include "rz_bitboard.cuh"
+
+namespace rz {
+namespace solver {
+
+constexpr int kSolverMaxEmpties = 12;
+constexpr int kMaxTasks = 256;   // > 12 * 11 second-ply positions
+constexpr int kMaxDepth = 24;
+
+struct Frame {
+    u64 own, enemy, moves;
+    int8_t best, alpha, beta, sign;  // sign: factor applied to this frame's value when it returns to its parent
+};
+
+// value of the position for the side to move (`own`, which has at least one legal move)
+__device__ inline int solve_subtree(u64 own, u64 enemy, bool exactly) {
+    Frame f[kMaxDepth];
+    int d = 0;
+    f[0].own = own; f[0].enemy = enemy; f[0].moves = find_correct_moves(own, enemy);
+    f[0].best = -100; f[0].alpha = -64; f[0].beta = 64; f[0].sign = 1;
+    while (true) {
+        Frame& F = f[d];
+        if (F.moves == 0 || (!exactly && F.best > 0) || (exactly && F.best >= F.beta)) {
+            if (d == 0) return F.best;
+            const int v = F.best * F.sign;
+            --d;
+            if (f[d].best < v) f[d].best = (int8_t)v;
+            continue;
+        }
+        const int a = ctz64(F.moves);
+        F.moves &= F.moves - 1;
+        const u64 fl = calc_flip(a, F.own, F.enemy);
+        const u64 own2 = (F.own ^ fl) | (1ULL << a), en2 = F.enemy ^ fl;
+        const int lo = F.best > F.alpha ? F.best : F.alpha;  // alpha-beta lower bound at this node (exact mode)
+        u64 m = find_correct_moves(en2, own2);
+        if (m) {  // opponent to move
+            if (d + 1 >= kMaxDepth) return F.best;  // cannot happen for <= kSolverMaxEmpties empties
+            Frame& C = f[++d];
+            C.own = en2; C.enemy = own2; C.moves = m; C.best = -100; C.sign = -1;
+            C.alpha = (int8_t)(-F.beta); C.beta = (int8_t)(-lo);
+        } else if ((m = find_correct_moves(own2, en2)) != 0) {  // pass: same side again, no sign flip
+            if (d + 1 >= kMaxDepth) return F.best;
+            Frame& C = f[++d];
+            C.own = own2; C.enemy = en2; C.moves = m; C.best = -100; C.sign = 1;
+            C.alpha = (int8_t)lo; C.beta = F.beta;
+        } else {
+            const int score = popc64(own2) - popc64(en2);
+            if (F.best < score) F.best = (int8_t)score;
+        }
+    }
+}
+
+// position after `own` plays at a: *terminal -> score for the mover; else the next position in ITS mover's frame and the
+// factor that converts its value back to the original mover's frame
+__device__ __forceinline__ bool after_move(u64 own, u64 enemy, int a, u64& nown, u64& nenemy, int& sign, int& score) {
+    const u64 fl = calc_flip(a, own, enemy);
+    const u64 own2 = (own ^ fl) | (1ULL << a), en2 = enemy ^ fl;
+    if (find_correct_moves(en2, own2)) { nown = en2; nenemy = own2; sign = -1; return false; }
+    if (find_correct_moves(own2, en2)) { nown = own2; nenemy = en2; sign = 1; return false; }
+    score = popc64(own2) - popc64(en2);
+    return true;
+}
+
+// Called by a full warp with identical arguments; `vals` is a per-warp scratch array of kMaxTasks int8 in shared memory.
+// Returns (move, score) in all lanes; move = -1: no legal move or position refused.
+__device__ inline void solve_warp(u64 own, u64 enemy, bool exactly, int8_t* vals, int lane, int& move_out, int& score_out) {
+    move_out = -1; score_out = -100;
+    const u64 legal = find_correct_moves(own, enemy);
+    if (!legal || 64 - popc64(own | enemy) > kSolverMaxEmpties) return;
+    // pass 1: every lane enumerates the grand-child tasks identically and solves those with index == lane (mod 32)
+    int t = 0;
+    for (u64 m1 = legal; m1; m1 &= m1 - 1) {
+        u64 o1, e1; int s1, sc1;
+        if (after_move(own, enemy, ctz64(m1), o1, e1, s1, sc1)) continue;
+        for (u64 m2 = find_correct_moves(o1, e1); m2; m2 &= m2 - 1) {
+            u64 o2, e2; int s2, sc2;
+            if (after_move(o1, e1, ctz64(m2), o2, e2, s2, sc2)) continue;
+            if ((t & 31) == lane && t < kMaxTasks) vals[t] = (int8_t)solve_subtree(o2, e2, exactly);
+            ++t;
+        }
+    }
+    __syncwarp();
+    if (t > kMaxTasks) return;  // refused (cannot happen within kSolverMaxEmpties)
+    // pass 2: the two top plies in the reference's order (all lanes compute the same thing)
+    t = 0;
+    int best = -100, best_move = -1;
+    for (u64 m1 = legal; m1; m1 &= m1 - 1) {
+        if (!exactly && best > 0) break;                      // :99 at the root
+        const int a1 = ctz64(m1);
+        u64 o1, e1; int s1, sc1;
+        int v1;
+        if (after_move(own, enemy, a1, o1, e1, s1, sc1)) {
+            v1 = sc1;
+        } else {
+            int b1 = -100;
+            bool stopped = false;
+            for (u64 m2 = find_correct_moves(o1, e1); m2; m2 &= m2 - 1) {
+                u64 o2, e2; int s2, sc2;
+                const bool term = after_move(o1, e1, ctz64(m2), o2, e2, s2, sc2);
+                const int v2 = term ? sc2 : s2 * (int)vals[t];
+                if (!term) ++t;
+                if (stopped) continue;                        // keep the task counter in step with pass 1
+                if (b1 < v2) b1 = v2;
+                if (!exactly && b1 > 0) stopped = true;       // :99 at the child
+            }
+            v1 = s1 * b1;
+        }
+        if (best < v1) { best = v1; best_move = a1; }
+    }
+    // tasks of root moves skipped by the early stop are simply not consumed
+    move_out = best_move; score_out = best;
+}
+
+}  // namespace solver
+}  // namespace rz

@@ -67,6 +67,8 @@ SIGNATURES = {
     "rz_step_dev": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "rz_step": (C.c_int, [u64p, u64p, u8p, u8p, u8p, u8p, i8p, u64p, sz]),
     "rz_dihedral_dev": (C.c_int, [vp, vp, vp, sz, vp]),
+    "rz_solve_dev": (C.c_int, [vp, vp, vp, vp, vp, sz, vp]),
+    "rz_solve": (C.c_int, [u64p, u64p, u8p, i8p, i8p, sz]),
     "rz_find_correct_moves_host": (C.c_uint64, [C.c_uint64, C.c_uint64]),
     "rz_calc_flip_host": (C.c_uint64, [C.c_int, C.c_uint64, C.c_uint64]),
     "rz_dihedral_host": (C.c_uint64, [C.c_uint64, C.c_int]),
