@@ -167,6 +167,10 @@ typedef struct rz_engine_cfg {
     int32_t max_sims_per_wave;      /* simulations one game may START in one wave (0 = 2 x parallel_search_num).  Bounds
                                        the work of a wave for games whose simulations end in terminal positions without
                                        needing the network (endgame), so no slot delays the whole batch. */
+    int32_t use_solver_turn;        /* PlayConfig.use_solver_turn (config.py:154): from this turn on the move is the exact
+                                       endgame solution (agent/player.py:100-103,150-161) and the ply is not training data;
+                                       0 = off.  Positions the device solver refuses (> 12 empties) are searched instead. */
+    int32_t use_solver_turn_in_simulation; /* :155, agent/player.py:237-251: WLD-solved nodes inside the search; 0 = off */
     int32_t max_searches_per_game;  /* sizes the per-game node arena: nodes = this x simulation_num_per_move;
                                        0 = 60 x min(thinking_loop, 2).  Rethinking (thinking_loop > 1) is skipped
                                        when the arena could no longer hold one search per remaining ply. */

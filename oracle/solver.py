@@ -17,8 +17,12 @@ class Solver:
         self.cache = {True: {}, False: {}}
         self.nodes = 0
 
+    MAX_EMPTIES = 12  # the device solver refuses larger positions (csrc/rz_solver.cuh), the analogue of the reference's timeout
+
     def solve(self, own, enemy, exactly=False):
-        """-> (move, score) for the side to move (own), or (None, None) if it has no move."""
+        """-> (move, score) for the side to move (own), or (None, None) if it has no move / the position is refused."""
+        if 64 - bb.bit_count(own | enemy) > self.MAX_EMPTIES:
+            return None, None
         move, score = self._f(own, enemy, exactly)
         return (None, None) if move < 0 else (move, score)
 

@@ -26,8 +26,27 @@
 #include <string.h>
 #include "rz_bitboard.cuh"
 #include "rz_net.cuh"
+#include "rz_solver.cuh"
 
 namespace rz {
+namespace solver {
+constexpr int kWarpsPerBlock = 4;
+// the engine's per-wave solver batch: the request count is produced on the device by the tick kernel
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) solve_counted_kernel(const u64* __restrict__ own, const u64* __restrict__ enemy,
+                                                                            const uint8_t* __restrict__ exactly, int8_t* __restrict__ move,
+                                                                            int8_t* __restrict__ score, const uint32_t* __restrict__ count) {
+    __shared__ int8_t vals[kWarpsPerBlock][kMaxTasks];
+    const uint32_t n = *count;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (uint32_t i = blockIdx.x * kWarpsPerBlock + w; i < n; i += gridDim.x * kWarpsPerBlock) {
+        int mv, sc;
+        solve_warp(own[i], enemy[i], exactly[i] != 0, vals[w], lane, mv, sc);
+        if (lane == 0) { move[i] = (int8_t)mv; score[i] = (int8_t)(mv < 0 ? 0 : sc); }
+        __syncwarp();
+    }
+}
+}  // namespace solver
+
 namespace eng {
 
 // ---- Philox4x32-10 (same streams as oracle/philox.py) ------------------------------------------------
@@ -76,7 +95,8 @@ struct Descent {
     uint32_t path[kMaxPath];  // edge index within the slot's arena | (mover_is_root << 31)
 };
 
-enum : uint8_t { PH_IDLE = 0, PH_SEARCH = 1, PH_DECIDE = 2, PH_NEWGAME = 3 };
+enum : uint8_t { PH_IDLE = 0, PH_SEARCH = 1, PH_DECIDE = 2, PH_NEWGAME = 3, PH_SOLVE = 4 /* waiting for the exact root solve */ };
+constexpr uint8_t kSolveMarker = 0xFF;  // Descent::dihedral of a descent that waits for a WLD solve instead of a network evaluation
 
 struct Slot {
     EnvState env;            // the real game
@@ -90,7 +110,10 @@ struct Slot {
     uint8_t resigned_mask, search_only, n_pending, n_parked;
     uint8_t pending[kMaxK], parked[kMaxK];
     u64 root_own, root_enemy;
-    uint8_t root_pid, black_net, cur_net, pad[5];  // black_net / cur_net: evaluation matches (two networks)
+    uint8_t root_pid, black_net, cur_net;  // black_net / cur_net: evaluation matches (two networks)
+    uint8_t root_req;         // 1: an exact root solve has to be put into this wave's solver batch
+    uint8_t pad[4];
+    uint32_t root_solve_index, n_solves, n_searched_plies, pad2;
 };
 
 struct Status {
@@ -102,7 +125,7 @@ struct Status {
 
 struct DevCfg {
     int G, S, K, vl, change_tau_turn, thinking_loop, required_visit, start_rethinking_turn, allowed_resign_turn;
-    int use_resign, share, max_plies, warm_start, sims_cap, two_nets;
+    int use_resign, share, max_plies, warm_start, sims_cap, two_nets, solver_turn, solver_sim_turn;
     float c_puct, noise_eps, alpha, resign_threshold, disable_resignation_rate;
     u64 seed, first_game_id, game_id_stride, max_games;
     uint32_t nodes_cap, edges_cap, hash_cap;  // per slot (hash_cap is a power of two)
@@ -123,6 +146,13 @@ struct DevPtrs {
     u64* batch_enemy;
     float* policy;         // [G*K][64]
     float* value;          // [G*K]
+    // endgame solver requests of the current wave (rows [slot0 * (K + 1), ...) per group) and their results
+    uint32_t* solve_count; // [2 groups] (64 words apart)
+    u64* sreq_own;
+    u64* sreq_enemy;
+    uint8_t* sreq_exact;
+    int8_t* sres_move;
+    int8_t* sres_score;
 };
 
 __device__ __forceinline__ uint32_t hash_key(u64 own, u64 enemy, uint32_t kpid) {
@@ -676,7 +706,7 @@ struct rz_engine {
     int n_groups;
     int group_slot0[3];
     int tick_impl;            // 0 = warp-per-game kernel (default), 1 = thread-per-slot cross-check (RZ_TICK_IMPL=thread)
-    void* arena[16];
+    void* arena[32];
     int n_arena;
     Status* h_status;     // pinned
     uint8_t* h_flags;     // pinned [G*2]
@@ -747,12 +777,21 @@ static int launch_wave(rz_engine* e) {
         const size_t rows = (size_t)(s1 - s0) * c.K;
         if (timed) RZ_CUDA_TRY(cudaEventRecord(ev[0], st));
         for (int net = 0; net <= c.two_nets; ++net) RZ_CUDA_TRY(cudaMemsetAsync(e->dp.batch_count + (net * 2 + g) * 64, 0, sizeof(uint32_t), st));
+        RZ_CUDA_TRY(cudaMemsetAsync(e->dp.solve_count + g * 64, 0, sizeof(uint32_t), st));
         if (e->tick_impl == 1)
             tick_kernel<<<(s1 - s0 + kTickThreads - 1) / kTickThreads, kTickThreads, 0, st>>>(c, e->dp, s0, s1, g);
         else
             tick_warp_kernel<<<(s1 - s0 + 1) / 2, kWarpTickThreads, 0, st>>>(c, e->dp, s0, s1, g);
         RZ_LAUNCH_CHECK();
         e->mcts_launches++;
+        if (c.solver_turn > 0 || c.solver_sim_turn > 0) {  // this wave's solver requests: runs underneath the other group's tower
+            const size_t r0 = (size_t)s0 * (c.K + 1);
+            solver::solve_counted_kernel<<<num_sms() * 4, solver::kWarpsPerBlock * 32, 0, st>>>(
+                e->dp.sreq_own + r0, e->dp.sreq_enemy + r0, e->dp.sreq_exact + r0, e->dp.sres_move + r0, e->dp.sres_score + r0,
+                e->dp.solve_count + g * 64);
+            RZ_LAUNCH_CHECK();
+            e->mcts_launches++;
+        }
         if (timed) RZ_CUDA_TRY(cudaEventRecord(ev[1], st));
         for (int net = 0; net <= c.two_nets; ++net) {
             uint32_t* count = e->dp.batch_count + (net * 2 + g) * 64;
@@ -821,6 +860,11 @@ int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net, int device, rz_engin
     e->group_slot0[2] = cfg->games;
     const char* ti = getenv("RZ_TICK_IMPL");
     e->tick_impl = (ti && strcmp(ti, "thread") == 0) ? 1 : 0;
+    if (e->tick_impl == 1 && (cfg->use_solver_turn > 0 || cfg->use_solver_turn_in_simulation > 0)) {
+        set_error("the thread-per-slot cross-check kernel does not implement the endgame solver hooks");
+        delete e;
+        return RZ_EINVAL;
+    }
     DevCfg& c = e->dc;
     c.G = cfg->games; c.S = cfg->simulation_num_per_move; c.K = cfg->parallel_search_num; c.vl = cfg->virtual_loss;
     c.change_tau_turn = cfg->change_tau_turn; c.thinking_loop = cfg->thinking_loop; c.required_visit = cfg->required_visit_to_decide_action;
@@ -828,6 +872,7 @@ int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net, int device, rz_engin
     c.use_resign = cfg->use_resign_threshold; c.share = cfg->share_mtcs_info; c.max_plies = cfg->max_plies > 0 ? cfg->max_plies : 64;
     c.warm_start = cfg->warm_start;
     c.two_nets = 0;
+    c.solver_turn = cfg->use_solver_turn; c.solver_sim_turn = cfg->use_solver_turn_in_simulation;
     c.sims_cap = cfg->max_sims_per_wave > 0 ? cfg->max_sims_per_wave : 2 * cfg->parallel_search_num;
     c.c_puct = cfg->c_puct; c.noise_eps = cfg->noise_eps; c.alpha = cfg->dirichlet_alpha; c.resign_threshold = cfg->resign_threshold;
     c.disable_resignation_rate = cfg->disable_resignation_rate;
@@ -862,6 +907,13 @@ int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net, int device, rz_engin
     if (!rc) rc = dev_alloc(e, (void**)&p.batch_enemy, (B + 2) * sizeof(u64), true);
     if (!rc) rc = dev_alloc(e, (void**)&p.policy, (B + 2) * 64 * sizeof(float), true);
     if (!rc) rc = dev_alloc(e, (void**)&p.value, (B + 2) * sizeof(float), true);
+    const size_t SR = G * (c.K + 1) + 8;
+    if (!rc) rc = dev_alloc(e, (void**)&p.solve_count, 1024, true);
+    if (!rc) rc = dev_alloc(e, (void**)&p.sreq_own, SR * sizeof(u64), true);
+    if (!rc) rc = dev_alloc(e, (void**)&p.sreq_enemy, SR * sizeof(u64), true);
+    if (!rc) rc = dev_alloc(e, (void**)&p.sreq_exact, SR, true);
+    if (!rc) rc = dev_alloc(e, (void**)&p.sres_move, SR, true);
+    if (!rc) rc = dev_alloc(e, (void**)&p.sres_score, SR, true);
     if (!rc && cudaMallocHost((void**)&e->h_status, sizeof(Status)) != cudaSuccess) { set_error("cudaMallocHost failed"); rc = RZ_ENOMEM; }
     if (!rc && cudaMallocHost((void**)&e->h_flags, G * 2) != cudaSuccess) { set_error("cudaMallocHost failed"); rc = RZ_ENOMEM; }
     for (int i = 0; i < 48 && !rc; ++i)

@@ -162,7 +162,32 @@ struct WCtx {
         return ctz64(m);
     }
 
-    // one simulation (oracle SelfPlayGame._run): 0 done, 1 pending, 2 parked
+    // ---- endgame solver hooks (agent/player.py:237-251); the WLD result of a position is cached in Node::pad:
+    //      bit 15 solved, bit 6 has-move, bits 0-5 move, bits 7-8 sign(score) + 1
+    __device__ static uint16_t wld_encode(int mv, int sc) {
+        const int sg = sc > 0 ? 2 : (sc < 0 ? 0 : 1);
+        return (uint16_t)(0x8000u | (mv >= 0 ? (0x40u | (uint32_t)mv) : 0u) | ((uint32_t)sg << 7));
+    }
+    // player.py:240-251 with the cached result; false when the reference's `if action:` fails (no move, or square 0)
+    __device__ bool apply_wld(int ni, const uint32_t* path, int path_len, bool mover_is_root) {
+        const Node nd = nodes[ni];
+        const int action = nd.pad & 63;
+        if (!(nd.pad & 0x40) || action == 0) return false;
+        const float sgn = (float)(((nd.pad >> 7) & 3) - 1);   // value for the side to move at this node
+        const int nl = popc64(nd.legal), r = popc64(nd.legal & ((1ULL << action) - 1));
+        Edge* ed = edges + nd.edge_base;
+        for (int i = lane; i < nl; i += 32) {
+            Edge e = ed[i];
+            e.p = i == r ? 1.f : 0.f;
+            if (i == r) { e.n += 1; e.w = e.w + sgn; }
+            ed[i] = e;
+        }
+        __syncwarp();
+        backup(path, path_len, mover_is_root ? sgn : -sgn);
+        return true;
+    }
+
+    // one simulation (oracle SelfPlayGame._run): 0 done, 1 pending (network), 2 parked, 3 pending (WLD solve)
     __device__ int run(int di) {
         Descent& D = desc[di];
         const int pid = sl.root_pid;
@@ -177,12 +202,28 @@ struct WCtx {
                 const Descent& o = desc[sl.pending[j]];
                 if (o.leaf_own == own && o.leaf_enemy == enemy) collide = true;
             }
+            int ni = find_node(own, enemy, kp);
+            if (c.solver_sim_turn > 0 && popc64(own | enemy) - 4 >= c.solver_sim_turn) {  // player.py:237-251
+                if (ni >= 0 && (nodes[ni].pad & 0x8000)) {
+                    __syncwarp();
+                    if (apply_wld(ni, D.path, path_len, np == pid)) return 0;
+                    // `if action:` failed: go on as if there were no solver
+                } else if (!collide) {  // not solved yet: request the solve, the simulation waits for it like for the network
+                    if (lane == 0) {
+                        D.black = black; D.white = white; D.next_player = (uint8_t)np; D.path_len = (uint8_t)path_len;
+                        D.dihedral = kSolveMarker;
+                        D.leaf_own = own; D.leaf_enemy = enemy;
+                        D.leaf_mover_is_root = (uint8_t)(np == pid);
+                    }
+                    __syncwarp();
+                    return 3;
+                }
+            }
             if (collide) {
                 if (lane == 0) { D.black = black; D.white = white; D.next_player = (uint8_t)np; D.path_len = (uint8_t)path_len; }
                 __syncwarp();
                 return 2;
             }
-            const int ni = find_node(own, enemy, kp);
             if (ni < 0 || !((nodes[ni].exp >> (pid - 1)) & 1)) {  // player.py:257
                 const U4 r = draw(c.seed, sl.game_id, sl.n_expand, P_DIHEDRAL, 0);
                 const int flip = u01(r.x) < 0.5 ? 4 : 0;
@@ -233,6 +274,18 @@ struct WCtx {
         const int t = D.dihedral;
         int ni = find_node(lown, lenemy, kp);
         if (ni < 0) ni = create_node(lown, lenemy, kp);
+        if (t == kSolveMarker) {  // result of a WLD solve requested in the previous wave
+            sl.n_solves++;
+            bool applied = false;
+            if (ni >= 0) {
+                if (lane == 0) nodes[ni].pad = wld_encode(p.sres_move[D.leaf_index], p.sres_score[D.leaf_index]);
+                __syncwarp();
+                applied = apply_wld(ni, D.path, D.path_len, D.leaf_mover_is_root != 0);
+            }
+            if (applied || ni < 0) dstat[di] = D_FREE;
+            else { dstat[di] = D_PARKED; sl.parked[sl.n_parked++] = (uint8_t)di; }  // continues from this node next wave
+            return;
+        }
         if (ni >= 0) {
             const Node nd = nodes[ni];
             const float* pol = p.policy + (size_t)D.leaf_index * 64;
@@ -288,7 +341,7 @@ struct WCtx {
                 const int di = sl.parked[j];
                 const int r = run(di);
                 if (r == 2) still[n_still++] = (uint8_t)di;
-                else if (r == 1) { dstat[di] = D_PENDING; sl.pending[sl.n_pending++] = (uint8_t)di; }
+                else if (r == 1 || r == 3) { dstat[di] = D_PENDING; sl.pending[sl.n_pending++] = (uint8_t)di; }
                 else dstat[di] = D_FREE;
             }
             while (sl.sims_started < sl.sims_target && sl.n_pending + n_still < c.K && started_wave < c.sims_cap) {
@@ -300,7 +353,7 @@ struct WCtx {
                 dstat[di] = D_PARKED;
                 const int r = run(di);
                 if (r == 2) still[n_still++] = (uint8_t)di;
-                else if (r == 1) { dstat[di] = D_PENDING; sl.pending[sl.n_pending++] = (uint8_t)di; }
+                else if (r == 1 || r == 3) { dstat[di] = D_PENDING; sl.pending[sl.n_pending++] = (uint8_t)di; }
                 else dstat[di] = D_FREE;
             }
             sl.n_parked = (uint8_t)n_still;
@@ -317,6 +370,59 @@ struct WCtx {
         sl.sims_started = 0; sl.sims_target = (uint32_t)c.S;
         sl.n_pending = 0; sl.n_parked = 0;
         sl.phase = PH_SEARCH;
+    }
+
+    // start of a ply (agent/player.py:95-109): from use_solver_turn on, ask the exact solver first (:100-103)
+    __device__ void begin_ply(u64 own, u64 enemy, int pid) {
+        if (c.solver_turn > 0 && popc64(own | enemy) - 4 >= c.solver_turn) {
+            sl.root_own = own; sl.root_enemy = enemy; sl.root_pid = (uint8_t)pid;
+            sl.root_req = 1;
+            sl.phase = PH_SOLVE;
+            return;
+        }
+        begin_search(own, enemy, pid);
+    }
+
+    // action_by_searching, agent/player.py:150-161, with the result of the exact solve requested in the previous wave
+    __device__ void consume_root_solve() {
+        const u64 own = sl.root_own, enemy = sl.root_enemy;
+        const int pid = sl.root_pid;
+        const int mv = p.sres_move[sl.root_solve_index], sc = p.sres_score[sl.root_solve_index];
+        sl.n_solves++;
+        if (mv < 0) { begin_search(own, enemy, pid); return; }  // refused (the reference: timeout) -> search as usual
+        const uint32_t kp = kpid_of(pid);
+        int ni = find_node(own, enemy, kp);
+        if (ni < 0) ni = create_node(own, enemy, kp);
+        if (ni < 0) { sl.phase = PH_IDLE; return; }
+        const Node nd = nodes[ni];
+        const float sgn = sc > 0 ? 1.f : (sc < 0 ? -1.f : 0.f);
+        const int nl = popc64(nd.legal), r = popc64(nd.legal & ((1ULL << mv) - 1));
+        Edge* ed = edges + nd.edge_base;
+        for (int i = lane; i < nl; i += 32) {
+            Edge e = ed[i];
+            e.p = i == r ? 1.f : 0.f;
+            if (i == r) { e.n = 999; e.w = sgn * 999.f; }
+            ed[i] = e;
+        }
+        __syncwarp();
+        if ((int)sl.ply >= c.max_plies) { fail(RZ_ECAPACITY); sl.phase = PH_IDLE; return; }
+        rz_ply& pl = p.plies[((size_t)s * 2 + sl.log_sel) * c.max_plies + sl.ply];
+        for (int sq = lane; sq < 64; sq += 32)
+            pl.n_visit[sq] = ((nd.legal >> sq) & 1ULL) ? ed[popc64(nd.legal & ((1ULL << sq) - 1))].n : 0;
+        if (lane == 0) {
+            pl.own = own; pl.enemy = enemy;
+            pl.player = (uint8_t)pid; pl.loops = 0; pl.pad[0] = pl.pad[1] = pl.pad[2] = 0;
+            pl.n = 999.f; pl.q = sgn;
+            pl.action = (int16_t)mv;
+            pl.recorded = 0;  // "not save move as play data", player.py:102
+            atomicAdd(&p.status->plies, 1ULL);
+        }
+        __syncwarp();
+        sl.ply++;
+        env_step(sl.env, mv);
+        if (sl.env.done) { finish_game(); return; }
+        const bool b2 = sl.env.next_player == 1;
+        begin_ply(b2 ? sl.env.black : sl.env.white, b2 ? sl.env.white : sl.env.black, sl.env.next_player);
     }
 
     __device__ void new_game() {
@@ -337,6 +443,7 @@ struct WCtx {
             __syncwarp();
         }
         sl.n_nodes = 0; sl.n_edges = 0; sl.n_expand = 0; sl.n_rootsel = 0; sl.n_sims = 0; sl.ply = 0; sl.tl = 0;
+        sl.n_searched_plies = 0; sl.n_solves = 0; sl.root_req = 0;
         sl.resigned_mask = 0; sl.search_only = 0;
         for (int k = 0; k < c.K; ++k) dstat[k] = D_FREE;
         sl.enable_resign = (uint8_t)((double)c.disable_resignation_rate <= u01(draw(c.seed, sl.game_id, 0, P_GAME, 0).x));
@@ -354,7 +461,7 @@ struct WCtx {
             if (sl.env.done) env_reset(sl.env);
             else if (sl.env.turn > 0) {
                 const bool b = sl.env.next_player == 1;
-                begin_search(b ? sl.env.black : sl.env.white, b ? sl.env.white : sl.env.black, sl.env.next_player);
+                begin_ply(b ? sl.env.black : sl.env.white, b ? sl.env.white : sl.env.black, sl.env.next_player);
             }
         }
     }
@@ -408,7 +515,7 @@ struct WCtx {
         int arg_n = 0;
         for (int i = 0; i < nl; ++i) { sum_n += ed[i].n; if (ed[i].n > ed[arg_n].n) arg_n = i; }
         const bool tau1 = turn < c.change_tau_turn;
-        const U4 r = draw(c.seed, sl.game_id, sl.ply * 16 + sl.tl, P_MOVE, 0);
+        const U4 r = draw(c.seed, sl.game_id, sl.n_searched_plies * 16 + sl.tl, P_MOVE, 0);
         const double uu = u53(r.x, r.y);
         int choice = arg_n;
         if (tau1) {
@@ -459,11 +566,12 @@ struct WCtx {
         }
         __syncwarp();
         sl.ply++;
+        sl.n_searched_plies++;
         sl.tl = 0;
         env_step(sl.env, resign ? -1 : action);
         if (sl.env.done) { finish_game(); return; }
         const bool b2 = sl.env.next_player == 1;
-        begin_search(b2 ? sl.env.black : sl.env.white, b2 ? sl.env.white : sl.env.black, sl.env.next_player);
+        begin_ply(b2 ? sl.env.black : sl.env.white, b2 ? sl.env.white : sl.env.black, sl.env.next_player);
     }
 };
 
@@ -480,9 +588,15 @@ __global__ void __launch_bounds__(kWarpTickThreads) tick_warp_kernel(const DevCf
     if (sl.phase == PH_IDLE) return;
     if (sl.phase == PH_SEARCH) {  // 1. consume the previous wave's evaluations in request order
         const uint32_t consumed = sl.n_pending;
-        for (int j = 0; j < (int)consumed; ++j) x.consume(sl.pending[j]);
+        uint32_t nn_consumed = 0;
+        for (int j = 0; j < (int)consumed; ++j) {
+            nn_consumed += x.desc[sl.pending[j]].dihedral != kSolveMarker;
+            x.consume(sl.pending[j]);
+        }
         sl.n_pending = 0;
-        if (consumed && lane == 0) atomicAdd(&p.status->expansions, (unsigned long long)consumed);
+        if (nn_consumed && lane == 0) atomicAdd(&p.status->expansions, (unsigned long long)nn_consumed);
+    } else if (sl.phase == PH_SOLVE && !sl.root_req) {
+        x.consume_root_solve();
     }
     for (int guard = 0; guard < 100000; ++guard) {  // 2. advance the state machine until the network is needed
         if (p.status->error != 0) break;
@@ -498,21 +612,39 @@ __global__ void __launch_bounds__(kWarpTickThreads) tick_warp_kernel(const DevCf
             if (p.mail_flag[(size_t)s * 2 + sl.log_sel]) break;
             x.new_game();
         } else {
-            break;
+            break;  // PH_SOLVE: the exact root solve is requested below and consumed in the next wave
         }
     }
     const int n_leaves = sl.phase == PH_SEARCH ? sl.n_pending : 0;
-    x.write_back();
-    // 3. gather (K3): one atomic per game, the lanes write the dihedral-transformed leaves of this game
-    uint32_t base = 0;
+    const uint32_t root_req = (sl.phase == PH_SOLVE && sl.root_req) ? 1u : 0u;
+    // 3. gather: network leaves (K3: dihedral-transformed bitboards) and solver requests go to their own compact batches
+    const bool mine = lane < n_leaves;
+    const bool is_solve = mine && x.desc[sl.pending[mine ? lane : 0]].dihedral == kSolveMarker;
+    const unsigned sv_mask = __ballot_sync(0xffffffffu, is_solve), nn_mask = __ballot_sync(0xffffffffu, mine && !is_solve);
+    const uint32_t n_nn = __popc(nn_mask), n_sv = __popc(sv_mask) + root_req;
     const uint32_t net = c.two_nets ? sl.cur_net : 0u;  // evaluation matches: every search is evaluated by the mover's network
-    if (lane == 0 && n_leaves > 0) base = atomicAdd(p.batch_count + (net * 2 + group) * 64, (uint32_t)n_leaves);
+    uint32_t base = 0, sbase = 0;
+    if (lane == 0 && n_nn > 0) base = atomicAdd(p.batch_count + (net * 2 + group) * 64, n_nn);
+    if (lane == 0 && n_sv > 0) sbase = atomicAdd(p.solve_count + group * 64, n_sv);
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (lane < n_leaves) {
+    sbase = __shfl_sync(0xffffffffu, sbase, 0);
+    if (root_req) { sl.root_solve_index = (uint32_t)slot0 * (uint32_t)(c.K + 1) + sbase + (n_sv - 1); sl.root_req = 0; }
+    x.write_back();
+    const uint32_t below = (1u << lane) - 1u;
+    if (mine && !is_solve) {
         Descent& d = x.desc[sl.pending[lane]];
-        const uint32_t at = net * (uint32_t)c.G * (uint32_t)c.K + (uint32_t)slot0 * (uint32_t)c.K + base + (uint32_t)lane;
+        const uint32_t at = net * (uint32_t)c.G * (uint32_t)c.K + (uint32_t)slot0 * (uint32_t)c.K + base + __popc(nn_mask & below);
         d.leaf_index = at;
         p.batch_own[at] = dihedral(d.leaf_own, d.dihedral);
         p.batch_enemy[at] = dihedral(d.leaf_enemy, d.dihedral);
+    } else if (is_solve) {
+        Descent& d = x.desc[sl.pending[lane]];
+        const uint32_t at = (uint32_t)slot0 * (uint32_t)(c.K + 1) + sbase + __popc(sv_mask & below);
+        d.leaf_index = at;
+        p.sreq_own[at] = d.leaf_own; p.sreq_enemy[at] = d.leaf_enemy; p.sreq_exact[at] = 0;
+    }
+    if (root_req && lane == 0) {
+        const uint32_t at = sl.root_solve_index;
+        p.sreq_own[at] = sl.root_own; p.sreq_enemy[at] = sl.root_enemy; p.sreq_exact[at] = 1;
     }
 }

@@ -11,7 +11,7 @@ EVAL_NET, EVAL_FAKE = 0, 1
 
 def engine_cfg_from_play_config(pc, pdc=None, games=1024, seed=0, eval_mode=EVAL_NET, net_impl=0, first_game_id=0,
                                 game_id_stride=1, max_games=0, warm_start=False, overlap_groups=0,
-                                max_searches_per_game=0):
+                                max_searches_per_game=0, use_solver=True):
     """Build an rz_engine_cfg from objects with the reference's PlayConfig / PlayDataConfig fields
     (config.py:116-166)."""
     cfg = _cabi.EngineCfg()
@@ -33,6 +33,8 @@ def engine_cfg_from_play_config(pc, pdc=None, games=1024, seed=0, eval_mode=EVAL
     cfg.overlap_groups = overlap_groups
     cfg.max_searches_per_game = max_searches_per_game
     cfg.max_sims_per_wave = int(getattr(pc, "max_sims_per_wave", 0) or 0)
+    cfg.use_solver_turn = int(getattr(pc, "use_solver_turn", 0) or 0) if use_solver else 0
+    cfg.use_solver_turn_in_simulation = int(getattr(pc, "use_solver_turn_in_simulation", 0) or 0) if use_solver else 0
     cfg.c_puct = float(pc.c_puct)
     cfg.noise_eps = float(pc.noise_eps)
     cfg.dirichlet_alpha = float(pc.dirichlet_alpha)

@@ -219,3 +219,36 @@ def test_evaluate_worker_with_real_networks(tmp_path):
     for g in games:
         replay_check(g)
     assert w.start(max_models=1) == 1 and not os.path.exists(ng_dir)      # evaluated, not promoted, directory removed
+
+
+@pytest.mark.parametrize("kw", [dict(use_solver_turn=52, use_solver_turn_in_simulation=52, simulation_num_per_move=24),
+                                dict(use_solver_turn=56, use_solver_turn_in_simulation=50, simulation_num_per_move=32, parallel_search_num=4),
+                                dict(use_solver_turn=0, use_solver_turn_in_simulation=51, simulation_num_per_move=20)])
+def test_full_games_with_endgame_solver_exact(kw):
+    """endgame solver hooks on the device (agent/player.py:100-103,150-161,237-251): exact root solves from
+    use_solver_turn on (plies not recorded) and WLD-solved nodes inside the search; whole games equal the oracle (which
+    equals the reference, tests/test_oracle.py::test_mcts_with_solver_exact_vs_reference)."""
+    pp = params(**kw)
+    n_games = 5
+    eng = make_engine(pp, games=3, seed=51, max_games=n_games)
+    eng.run(finished_target=n_games)
+    games = sorted(eng.poll(), key=lambda g: g["game_id"])
+    eng.close()
+    assert len(games) == n_games
+    solved_total = 0
+    for g in games:
+        replay_check(g)
+        o = mcts.SelfPlayGame(pp, onn.FakeNetAPI(), seed=51, game_id=g["game_id"]).play()
+        theirs = sorted(o.plies + o.solved_plies, key=lambda r: r["turn"])
+        assert len(g["plies"]) == len(theirs)
+        for mine, ref in zip(g["plies"], theirs):
+            assert (mine["own"], mine["enemy"], mine["pid"], mine["action"]) == (ref["own"], ref["enemy"], ref["pid"], ref["action"])
+            assert mine["recorded"] == ("N" in ref)
+            if "N" in ref:
+                assert list(mine["N"]) == list(ref["N"]) and mine["loops"] == ref["loops"]
+            else:
+                solved_total += 1
+                assert mine["n"] == 999.0 and mine["q"] == ref["q"]
+        assert g["winner"] == o.env.winner and g["expansions"] == o.n_expand
+    if kw["use_solver_turn"]:
+        assert solved_total > 0
