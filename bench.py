@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--games", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sims", type=int, default=400, help="simulation_num_per_move (BASELINE config 3 uses 800 with --games 8192)")
+    ap.add_argument("--solver", action="store_true", help="with --full-games: ch5 default use_solver_turn = use_solver_turn_in_simulation = 50")
     ap.add_argument("--groups", type=int, default=0, help="engine overlap groups (0 = auto, 1 = no overlap: clean per-kernel timing)")
     ap.add_argument("--full-games", type=int, default=0, metavar="G",
                     help="calibration: play G complete games from a cold start and write gpurun_out/full_games.json")
@@ -199,6 +200,8 @@ def main():
         return E.Engine(cfg, net, local)
 
     if args.full_games:
+        if args.solver:
+            pp.use_solver_turn = pp.use_solver_turn_in_simulation = 50
         cfg = E.engine_cfg_from_play_config(pp, games=args.full_games, seed=20260922, eval_mode=E.EVAL_NET, max_games=args.full_games)
         eng = E.Engine(cfg, net, local)
         t0 = time.perf_counter()
@@ -210,9 +213,10 @@ def main():
                    simulations_per_game=sum(g["simulations"] for g in gs) / len(gs), plies_per_game=sum(len(g["plies"]) for g in gs) / len(gs),
                    black_wins=sum(g["winner"] == 1 for g in gs), white_wins=sum(g["winner"] == 2 for g in gs), draws=sum(g["winner"] == 3 for g in gs),
                    seconds=dt, games_per_sec_cold_start=len(gs) / dt, waves=st["waves"], max_nodes_used=st["max_nodes_used"],
-                   max_edges_used=st["max_edges_used"], workload=workload_config(args)["workload"])
+                   max_edges_used=st["max_edges_used"], workload=workload_config(args)["workload"].replace("solver=off", "solver=on(50/50)" if args.solver else "solver=off"),
+                   recorded_plies_per_game=sum(sum(1 for p in g["plies"] if p["recorded"]) for g in gs) / len(gs))
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", "full_games.json"), "w") as f:
+        with open(os.path.join(ROOT, "gpurun_out", "full_games_solver.json" if args.solver else "full_games.json"), "w") as f:
             json.dump(out, f)
         print(json.dumps(out), flush=True)
         return
