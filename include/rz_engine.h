@@ -171,6 +171,9 @@ typedef struct rz_engine_cfg {
                                        endgame solution (agent/player.py:100-103,150-161) and the ply is not training data;
                                        0 = off.  Positions the device solver refuses (> 12 empties) are searched instead. */
     int32_t use_solver_turn_in_simulation; /* :155, agent/player.py:237-251: WLD-solved nodes inside the search; 0 = off */
+    int32_t reset_mtcs_info_per_game; /* PlayConfig.reset_mtcs_info_per_game (config.py:131; worker/self_play.py:111-134): a
+                                       slot keeps its statistics for this many consecutive games (0 / 1: every game starts
+                                       empty, ch5.yml; mini.yml uses 3).  Arenas grow by the same factor. */
     int32_t max_searches_per_game;  /* sizes the per-game node arena: nodes = this x simulation_num_per_move;
                                        0 = 60 x min(thinking_loop, 2).  Rethinking (thinking_loop > 1) is skipped
                                        when the arena could no longer hold one search per remaining ply. */

@@ -52,6 +52,7 @@ class PlayParams:
         self.save_policy_of_tau_1 = True
         self.use_solver_turn = 0                # config.py:154; 0 = solver off (agent/player.py:100)
         self.use_solver_turn_in_simulation = 0  # config.py:155 (agent/player.py:237-238)
+        self.reset_mtcs_info_per_game = 1       # config.py:131
         self.max_sims_per_wave = 0  # engine knob (0 = 2 * parallel_search_num): simulations started per game per wave
         for k, v in kw.items():
             if not hasattr(self, k):
@@ -137,7 +138,7 @@ class SelfPlayGame:
     """One self-play game: both players, shared (or separate) statistics, compact per-ply log."""
     deadline = None  # optional wall-clock bound used by the CPU-baseline timing (oracle/selfplay_cpu.py)
 
-    def __init__(self, pp, api, seed=0, game_id=0, noise_rng=None, api_b=None, black_net=0):
+    def __init__(self, pp, api, seed=0, game_id=0, noise_rng=None, api_b=None, black_net=0, table=None):
         """api_b / black_net: evaluation matches (worker/evaluate.py:66-96) -- the player of colour `pid` is
         evaluated by `api` when it plays for network 0 and by `api_b` when it plays for network 1; black_net says
         which network has the black stones."""
@@ -145,7 +146,11 @@ class SelfPlayGame:
         self.api_b, self.black_net = api_b, black_net
         self.noise_rng = noise_rng or np.random.default_rng((seed, game_id))
         self.env = bb.Env().reset()
-        self.table = {}
+        # reset_mtcs_info_per_game > 1 (worker/self_play.py:111-134): statistics carried over from the previous game of the
+        # same worker; the new players treat every position with a prior as expanded (player.py:47)
+        self.table = table if table is not None else {}
+        for node in self.table.values():
+            node.exp = 3
         self.n_expand = 0      # leaves sent to the evaluator (== "node expansions")
         self.n_rootsel = 0
         self.n_sims = 0

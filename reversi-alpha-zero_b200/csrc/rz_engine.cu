@@ -125,7 +125,7 @@ struct Status {
 
 struct DevCfg {
     int G, S, K, vl, change_tau_turn, thinking_loop, required_visit, start_rethinking_turn, allowed_resign_turn;
-    int use_resign, share, max_plies, warm_start, sims_cap, two_nets, solver_turn, solver_sim_turn;
+    int use_resign, share, max_plies, warm_start, sims_cap, two_nets, solver_turn, solver_sim_turn, keep_games;
     float c_puct, noise_eps, alpha, resign_threshold, disable_resignation_rate;
     u64 seed, first_game_id, game_id_stride, max_games;
     uint32_t nodes_cap, edges_cap, hash_cap;  // per slot (hash_cap is a power of two)
@@ -860,8 +860,8 @@ int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net, int device, rz_engin
     e->group_slot0[2] = cfg->games;
     const char* ti = getenv("RZ_TICK_IMPL");
     e->tick_impl = (ti && strcmp(ti, "thread") == 0) ? 1 : 0;
-    if (e->tick_impl == 1 && (cfg->use_solver_turn > 0 || cfg->use_solver_turn_in_simulation > 0)) {
-        set_error("the thread-per-slot cross-check kernel does not implement the endgame solver hooks");
+    if (e->tick_impl == 1 && (cfg->use_solver_turn > 0 || cfg->use_solver_turn_in_simulation > 0 || cfg->reset_mtcs_info_per_game > 1)) {
+        set_error("the thread-per-slot cross-check kernel implements neither the endgame solver hooks nor reset_mtcs_info_per_game > 1");
         delete e;
         return RZ_EINVAL;
     }
@@ -872,6 +872,7 @@ int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net, int device, rz_engin
     c.use_resign = cfg->use_resign_threshold; c.share = cfg->share_mtcs_info; c.max_plies = cfg->max_plies > 0 ? cfg->max_plies : 64;
     c.warm_start = cfg->warm_start;
     c.two_nets = 0;
+    c.keep_games = cfg->reset_mtcs_info_per_game > 1 ? cfg->reset_mtcs_info_per_game : 1;
     c.solver_turn = cfg->use_solver_turn; c.solver_sim_turn = cfg->use_solver_turn_in_simulation;
     c.sims_cap = cfg->max_sims_per_wave > 0 ? cfg->max_sims_per_wave : 2 * cfg->parallel_search_num;
     c.c_puct = cfg->c_puct; c.noise_eps = cfg->noise_eps; c.alpha = cfg->dirichlet_alpha; c.resign_threshold = cfg->resign_threshold;
@@ -880,7 +881,7 @@ int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net, int device, rz_engin
     // every simulation creates at most one node; a game has at most 60 searched plies
     const uint64_t searches = cfg->max_searches_per_game > 0 ? (uint64_t)cfg->max_searches_per_game
                                                               : (uint64_t)60 * (c.thinking_loop > 2 ? 2 : c.thinking_loop);
-    uint64_t nodes = searches * c.S + 64;
+    uint64_t nodes = searches * c.S * (uint64_t)c.keep_games + 64;
     if (nodes > 0xFFFF0) nodes = 0xFFFF0;
     c.nodes_cap = (uint32_t)nodes;
     c.edges_cap = c.nodes_cap * 14;
@@ -1016,7 +1017,7 @@ int rz_engine_set_simulation_num(rz_engine* e, int32_t sims) {
     RZ_REQUIRE(e && sims >= 1, "rz_engine_set_simulation_num: bad argument");
     const uint64_t searches = e->cfg.max_searches_per_game > 0 ? (uint64_t)e->cfg.max_searches_per_game
                                                                   : (uint64_t)60 * (e->dc.thinking_loop > 2 ? 2 : e->dc.thinking_loop);
-    uint64_t need = searches * sims + 64;
+    uint64_t need = searches * sims * (uint64_t)e->dc.keep_games + 64;
     RZ_REQUIRE(need <= e->dc.nodes_cap, "simulation count %d exceeds the arenas sized at creation", sims);
     e->dc.S = sims;
     e->cfg.simulation_num_per_move = sims;

@@ -436,13 +436,21 @@ struct WCtx {
         sl.black_net = c.two_nets ? (uint8_t)(local & 1) : (uint8_t)0;
         sl.games_played++;
         env_reset(sl.env);
-        sl.gen = sl.gen + 1;
-        if (sl.gen >= 4096) {
-            for (uint32_t i = lane; i < c.hash_cap; i += 32) hash[i] = 0;
-            sl.gen = 1;
+        if (c.keep_games > 1 && (sl.games_played - 1) % (u64)c.keep_games != 0) {
+            // reset_mtcs_info_per_game > 1 (worker/self_play.py:111-134): the statistics of the previous game stay; the two
+            // new players regard every position that has a prior as expanded (player.py:47 expanded = set(var_p.keys()))
+            for (uint32_t i = lane; i < sl.n_nodes; i += 32) nodes[i].exp = 3;
             __syncwarp();
+        } else {
+            sl.gen = sl.gen + 1;
+            if (sl.gen >= 4096) {
+                for (uint32_t i = lane; i < c.hash_cap; i += 32) hash[i] = 0;
+                sl.gen = 1;
+                __syncwarp();
+            }
+            sl.n_nodes = 0; sl.n_edges = 0;
         }
-        sl.n_nodes = 0; sl.n_edges = 0; sl.n_expand = 0; sl.n_rootsel = 0; sl.n_sims = 0; sl.ply = 0; sl.tl = 0;
+        sl.n_expand = 0; sl.n_rootsel = 0; sl.n_sims = 0; sl.ply = 0; sl.tl = 0;
         sl.n_searched_plies = 0; sl.n_solves = 0; sl.root_req = 0;
         sl.resigned_mask = 0; sl.search_only = 0;
         for (int k = 0; k < c.K; ++k) dstat[k] = D_FREE;

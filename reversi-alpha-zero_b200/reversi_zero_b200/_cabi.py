@@ -32,7 +32,7 @@ class EngineCfg(C.Structure):
         "games", "simulation_num_per_move", "parallel_search_num", "virtual_loss", "change_tau_turn", "thinking_loop",
         "required_visit_to_decide_action", "start_rethinking_turn", "allowed_resign_turn", "use_resign_threshold",
         "share_mtcs_info", "eval_mode", "net_impl", "max_plies", "warm_start", "overlap_groups", "max_sims_per_wave", "use_solver_turn", "use_solver_turn_in_simulation",
-        "max_searches_per_game")] + [(n, C.c_float) for n in (
+        "reset_mtcs_info_per_game", "max_searches_per_game")] + [(n, C.c_float) for n in (
             "c_puct", "noise_eps", "dirichlet_alpha", "resign_threshold", "disable_resignation_rate")] + [
         (n, C.c_uint64) for n in ("seed", "first_game_id", "game_id_stride", "max_games")]
 

@@ -33,6 +33,7 @@ def engine_cfg_from_play_config(pc, pdc=None, games=1024, seed=0, eval_mode=EVAL
     cfg.overlap_groups = overlap_groups
     cfg.max_searches_per_game = max_searches_per_game
     cfg.max_sims_per_wave = int(getattr(pc, "max_sims_per_wave", 0) or 0)
+    cfg.reset_mtcs_info_per_game = int(getattr(pc, "reset_mtcs_info_per_game", 1) or 1) if cfg.share_mtcs_info else 1
     cfg.use_solver_turn = int(getattr(pc, "use_solver_turn", 0) or 0) if use_solver else 0
     cfg.use_solver_turn_in_simulation = int(getattr(pc, "use_solver_turn_in_simulation", 0) or 0) if use_solver else 0
     cfg.c_puct = float(pc.c_puct)

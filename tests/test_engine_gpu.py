@@ -252,3 +252,31 @@ def test_full_games_with_endgame_solver_exact(kw):
         assert g["winner"] == o.env.winner and g["expansions"] == o.n_expand
     if kw["use_solver_turn"]:
         assert solved_total > 0
+
+
+def test_reset_mtcs_info_per_game():
+    """PlayConfig.reset_mtcs_info_per_game = 3 (config/mini.yml:13): a slot keeps its statistics across three consecutive
+    games (worker/self_play.py:111-134); whole games equal the oracle that is handed the previous game's table."""
+    pp = params(simulation_num_per_move=20, change_tau_turn=0)
+    pp.reset_mtcs_info_per_game = 3
+    n_games = 8  # 2 slots x 4 games: games 0,2,4 / 1,3,5 share a table, games 6 / 7 start a new one
+    eng = make_engine(pp, games=2, seed=61, max_games=n_games)
+    eng.run(finished_target=n_games)
+    games = {g["game_id"]: g for g in eng.poll()}
+    st = eng.stats()
+    eng.close()
+    assert len(games) == n_games
+    for slot in range(2):
+        table = None
+        for k in range(4):
+            gid = slot + 2 * k
+            if k % 3 == 0:
+                table = None
+            o = mcts.SelfPlayGame(pp, onn.FakeNetAPI(), seed=61, game_id=gid, table=table).play()
+            table = o.table
+            g = games[gid]
+            replay_check(g)
+            assert [(p["own"], p["enemy"], p["action"], list(p["N"])) for p in g["plies"]] == \
+                   [(p["own"], p["enemy"], p["action"], list(p["N"])) for p in o.plies], gid
+            assert g["expansions"] == o.n_expand
+    assert st["max_nodes_used"] > 0
