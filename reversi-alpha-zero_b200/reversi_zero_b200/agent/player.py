@@ -39,6 +39,8 @@ class ReversiPlayer:
                                            eval_mode=EVAL_NET if model is not None else EVAL_FAKE)
         self.engine = Engine(ecfg, model, device)
         self._fresh = True
+        self._engine_sims = int(self.play_config.simulation_num_per_move)
+        self.solver = None
         self.moves = []
         self.thinking_history = {}
         self.resigned = False
@@ -55,8 +57,23 @@ class ReversiPlayer:
         return self.action_with_evaluation(own, enemy, callback_in_mtcs=callback_in_mtcs).action
 
     def _search(self, own, enemy):
-        n, w = self.engine.search_root(int(own), int(enemy), 1, 0, keep_tree=not self._fresh)
-        self._fresh = False
+        """simulation_num_per_move simulations from (own, enemy); with a CallbackInMCTS the search runs in chunks of
+        `per_sim` simulations (the tree is kept between chunks) and reports (q, n) after each, like
+        agent/player.py:212-214; stop_thinking() ends it early (:206-208)."""
+        total = int(self.play_config.simulation_num_per_move)
+        cb = self.callback_in_mtcs
+        chunk = int(cb.per_sim) if cb and cb.per_sim > 0 else total
+        done, n, w = 0, None, None
+        while done < total and not (self.requested_stop_thinking and done > 0):
+            step = min(chunk, total - done)
+            if step != self._engine_sims:
+                self.engine.set_simulation_num(step)
+                self._engine_sims = step
+            n, w = self.engine.search_root(int(own), int(enemy), 1, 0, keep_tree=not self._fresh)
+            self._fresh = False
+            done += step
+            if cb and cb.per_sim > 0:
+                cb.callback(list(w / (n + 1e-5)), list(n))
         return n.astype(np.float64), w.astype(np.float64)
 
     def action_with_evaluation(self, own, enemy, callback_in_mtcs=None):
@@ -65,6 +82,16 @@ class ReversiPlayer:
         turn = bit_count(own) + bit_count(enemy) - 4
         self.callback_in_mtcs = callback_in_mtcs
         self.requested_stop_thinking = False
+        if pc.use_solver_turn and turn >= pc.use_solver_turn:  # action_by_searching, agent/player.py:100-103,150-161
+            if self.solver is None:
+                from ..lib.reversi_solver import ReversiSolver
+                self.solver = ReversiSolver()
+            mv, score = self.solver.solve(own, enemy, 1, exactly=True)
+            if mv is not None:
+                policy = np.zeros(64)
+                policy[mv] = 1
+                self.thinking_history[(own, enemy)] = HistoryItem(mv, policy, None, None, None, None)
+                return ActionWithEvaluation(action=mv, n=999, q=float(np.sign(score)))  # not saved as play data
         n = w = None
         for tl in range(pc.thinking_loop):
             if turn > 0:

@@ -88,6 +88,12 @@ def test_reversi_player_mirror_plays_a_game(tmp_path):
         a = pl.action(own, enemy)
         assert (ob.find_correct_moves(own, enemy) >> a) & 1
         env.step(a)
+    # CallbackInMCTS (agent/player.py:21,212-214): (q, n) reported every per_sim simulations
+    from reversi_zero_b200.agent.player import CallbackInMCTS
+    seen = []
+    p3 = ReversiPlayer(cfg, None, seed=3)
+    p3.action(0x0000001000000000, 0x0000000818080000, callback_in_mtcs=CallbackInMCTS(10, lambda q, n: seen.append(sum(n))))
+    assert len(seen) == 3 and seen == sorted(seen) and seen[-1] >= 29
     black.finish_game(1); white.finish_game(-1)
     assert len(black.moves) % 8 == 0 and black.moves[0][2] == 1 and white.moves[-1][2] == -1
     assert env.turn <= 60 and env.winner is not None
