@@ -1,0 +1,91 @@
+"""CPU tests of the host-side logic of the worker mirrors (no GPU calls): simulation-count schedule and
+.force-sim override (worker/self_play.py:262-272), resignation-threshold auto-tuner (:219-260), GGF move text
+(:275-299, lib/ggf.py), config overlay of the reference's YAML structure, evaluation play-config defaults
+(config.py:103-113), rank-strided game ids."""
+import os
+import types
+
+import pytest
+
+from reversi_zero_b200 import _cabi
+from reversi_zero_b200.config import Config, create_config
+from reversi_zero_b200.worker.self_play import SelfPlayWorker, read_as_int
+from reversi_zero_b200.worker.evaluate import eval_play_config
+from reversi_zero_b200.parallel import rank_game_ids
+
+
+class FakeEngine:
+    def __init__(self):
+        self.thresholds = []
+
+    def set_resign_threshold(self, t):
+        self.thresholds.append(t)
+
+
+def make_worker(tmp_path):
+    cfg = Config(project_dir=str(tmp_path), data_dir=str(tmp_path / "data"))
+    cfg.resource.create_directories()
+    w = SelfPlayWorker(cfg)
+    w.engine = FakeEngine()
+    return cfg, w
+
+
+def test_simulation_schedule_and_force_file(tmp_path):
+    cfg, w = make_worker(tmp_path)
+    assert [w.decide_simulation_num_per_move(i) for i in (0, 299, 300, 1999, 2000, 10 ** 6)] == [8, 8, 50, 50, 200, 200]
+    cfg.play.schedule_of_simulation_num_per_move = [[0, 400]]
+    assert w.decide_simulation_num_per_move(12345) == 400
+    with open(cfg.resource.force_simulation_num_file, "wt") as f:
+        f.write("123\n")
+    assert w.decide_simulation_num_per_move(0) == 123 and read_as_int(cfg.resource.force_simulation_num_file) == 123
+    with open(cfg.resource.force_simulation_num_file, "wt") as f:
+        f.write("not a number")
+    assert w.decide_simulation_num_per_move(0) == 400
+
+
+def game(winner, resigned_mask, resign_enabled):
+    return types.SimpleNamespace(winner=winner, resigned_mask=resigned_mask, resign_enabled=resign_enabled)
+
+
+def test_resign_threshold_tuner(tmp_path):
+    cfg, w = make_worker(tmp_path)
+    assert cfg.play.resign_threshold == -0.9
+    # 100 test games (resignation disabled), 10 false positives (the eventual winner wanted to resign): rate 0.10 >= 0.05
+    for i in range(100):
+        w._finish_game(game(winner=1, resigned_mask=1 if i < 10 else 2, resign_enabled=0))
+    assert abs(cfg.play.resign_threshold - (-0.91)) < 1e-12 and w.engine.thresholds == [cfg.play.resign_threshold]
+    assert w.resign_test_game_count == 0
+    # next 100 without false positives: threshold moves back up
+    for i in range(100):
+        w._finish_game(game(winner=2, resigned_mask=1, resign_enabled=0))
+    assert abs(cfg.play.resign_threshold - (-0.90)) < 1e-12
+    # games with resignation enabled never count
+    w._finish_game(game(winner=3, resigned_mask=3, resign_enabled=1))
+    assert w.resign_test_game_count == 0
+
+
+def test_ggf_line(tmp_path):
+    cfg, w = make_worker(tmp_path)
+    P = _cabi.Ply
+    plies = []
+    for action, player, q, n in ((19, 1, 0.25, 10.0), (18, 2, -0.5, 7.0), (17, 2, 0.0, 3.0), (-1, 1, 0.0, 0.0)):
+        p = P(); p.action, p.player, p.q, p.n = action, player, q, n
+        plies.append(p)
+    line = w._ggf_of(None, plies)
+    # black C4, white C3, black passes (white moves twice in a row), white C2; the resignation is not a move
+    assert "B[C4/2.5/10.0]W[C3/-5.0/7.0]B[PA]W[C2/0.0/3.0];)" in line and line.startswith("(;GM[Othello]PC[RAZSelf]")
+
+
+def test_config_overlay_like_reference_yaml():
+    cfg = create_config({"type": "mini", "model": {"cnn_filter_num": 16, "res_layer_num": 1}, "play": {"c_puct": 5, "thinking_loop": 2},
+                         "play_data": {"nb_game_in_file": 2}, "trainer": {"batch_size": 256}, "eval": {"game_num": 100, "play_config": {"c_puct": 1}}})
+    assert (cfg.model.cnn_filter_num, cfg.model.value_fc_size, cfg.play.c_puct, cfg.play.virtual_loss) == (16, 256, 5, 3)
+    assert cfg.trainer == {"batch_size": 256}            # sections the self-play path does not model stay as given
+    pc = eval_play_config(cfg)
+    assert (pc.simulation_num_per_move, pc.noise_eps, pc.change_tau_turn, pc.c_puct, pc.thinking_loop) == (400, 0, 0, 1, 1)
+    assert pc.share_mtcs_info_in_self_play is False and cfg.play.noise_eps == 0.25
+
+
+def test_rank_game_ids_partition():
+    ids = [set(rank_game_ids(r, 4, 100, slots=5, games_per_slot=3)) for r in range(4)]
+    assert all(len(s) == 15 for s in ids) and set().union(*ids) == set(range(100, 160))
