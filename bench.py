@@ -83,7 +83,7 @@ def expansions_per_game():
     profiles/; the fallback is the value probed on the reference (21 256 at sim = 400)."""
     sims = PLAY_KW["simulation_num_per_move"]
     try:
-        with open(os.path.join(ROOT, "profiles", "full_games.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "full_games_solver_on.json" if PLAY_KW.get("use_solver_turn") else "full_games.json")) as f:
             d = json.load(f)
         if "sims=%d " % sims in d["workload"]:
             return float(d["expansions_per_game"]), "measured: profiles/full_games.json (%d complete games)" % d["games"]
@@ -129,7 +129,7 @@ def run_reference(args):
 
 def workload_config(args, **extra):
     c = dict(workload="selfplay ch5 net (256x10, random-init) G=%d games/GPU sims=%d K=8 c_puct=5 vl=3 noise=0.25 tau_turn=4 "
-                      "thinking_loop=1 solver=off resign=off" % (args.games, args.sims),
+                      "thinking_loop=1 solver=%s resign=off" % (args.games, args.sims, "on(50/50)" if PLAY_KW.get("use_solver_turn") else "off"),
              games_per_gpu=args.games, simulation_num_per_move=PLAY_KW["simulation_num_per_move"],
              l2="leaf batch + per-game trees (>20 GB) exceed L2; weights (23.7 MB fp16) are L2-resident by design",
              step="one wave = MCTS tick kernel + tcgen05 tower launch over the leaf batch", parallelism=f"dp{args.gpus} (games sharded by rank)")
@@ -152,6 +152,8 @@ def main():
                     help="calibration: play G complete games from a cold start and write gpurun_out/full_games.json")
     args = ap.parse_args()
     PLAY_KW["simulation_num_per_move"] = args.sims
+    if args.solver:  # ch5.yml's default solver settings instead of the benchmark configuration (solver off)
+        PLAY_KW["use_solver_turn"] = PLAY_KW["use_solver_turn_in_simulation"] = 50
     if args.impl == "reference":
         if args.steps > 4:
             args.steps, args.warmup = 2, 0  # each step is a 12 s time-bounded CPU sample (+ process start-up)
@@ -200,8 +202,6 @@ def main():
         return E.Engine(cfg, net, local)
 
     if args.full_games:
-        if args.solver:
-            pp.use_solver_turn = pp.use_solver_turn_in_simulation = 50
         cfg = E.engine_cfg_from_play_config(pp, games=args.full_games, seed=20260922, eval_mode=E.EVAL_NET, max_games=args.full_games)
         eng = E.Engine(cfg, net, local)
         t0 = time.perf_counter()
@@ -213,7 +213,7 @@ def main():
                    simulations_per_game=sum(g["simulations"] for g in gs) / len(gs), plies_per_game=sum(len(g["plies"]) for g in gs) / len(gs),
                    black_wins=sum(g["winner"] == 1 for g in gs), white_wins=sum(g["winner"] == 2 for g in gs), draws=sum(g["winner"] == 3 for g in gs),
                    seconds=dt, games_per_sec_cold_start=len(gs) / dt, waves=st["waves"], max_nodes_used=st["max_nodes_used"],
-                   max_edges_used=st["max_edges_used"], workload=workload_config(args)["workload"].replace("solver=off", "solver=on(50/50)" if args.solver else "solver=off"),
+                   max_edges_used=st["max_edges_used"], workload=workload_config(args)["workload"],
                    recorded_plies_per_game=sum(sum(1 for p in g["plies"] if p["recorded"]) for g in gs) / len(gs))
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", "full_games_solver.json" if args.solver else "full_games.json"), "w") as f:
