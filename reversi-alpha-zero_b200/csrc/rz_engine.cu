@@ -34,13 +34,15 @@ constexpr int kWarpsPerBlock = 4;
 // the engine's per-wave solver batch: the request count is produced on the device by the tick kernel
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) solve_counted_kernel(const u64* __restrict__ own, const u64* __restrict__ enemy,
                                                                             const uint8_t* __restrict__ exactly, int8_t* __restrict__ move,
-                                                                            int8_t* __restrict__ score, const uint32_t* __restrict__ count) {
+                                                                            int8_t* __restrict__ score, const uint32_t* __restrict__ count,
+                                                                            u64* tt_base) {
     __shared__ int8_t vals[kWarpsPerBlock][kMaxTasks];
     const uint32_t n = *count;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const TT tt{tt_base + ((size_t)blockIdx.x * kWarpsPerBlock + w) * kTtEntries * kTtWordsPerEntry};
     for (uint32_t i = blockIdx.x * kWarpsPerBlock + w; i < n; i += gridDim.x * kWarpsPerBlock) {
         int mv, sc;
-        solve_warp(own[i], enemy[i], exactly[i] != 0, vals[w], lane, mv, sc);
+        solve_warp(own[i], enemy[i], exactly[i] != 0, vals[w], lane, mv, sc, tt);
         if (lane == 0) { move[i] = (int8_t)mv; score[i] = (int8_t)(mv < 0 ? 0 : sc); }
         __syncwarp();
     }
@@ -153,6 +155,7 @@ struct DevPtrs {
     uint8_t* sreq_exact;
     int8_t* sres_move;
     int8_t* sres_score;
+    u64* solver_tt;        // per-warp transposition tables of the solver kernel, one set per slot group
 };
 
 __device__ __forceinline__ uint32_t hash_key(u64 own, u64 enemy, uint32_t kpid) {
@@ -705,6 +708,7 @@ struct rz_engine {
     cudaStream_t stream2;     // group 1 (tick of one group overlaps the network launch of the other)
     int n_groups;
     int group_slot0[3];
+    size_t solver_tt_words_per_group;
     int tick_impl;            // 0 = warp-per-game kernel (default), 1 = thread-per-slot cross-check (RZ_TICK_IMPL=thread)
     void* arena[32];
     int n_arena;
@@ -788,7 +792,7 @@ static int launch_wave(rz_engine* e) {
             const size_t r0 = (size_t)s0 * (c.K + 1);
             solver::solve_counted_kernel<<<num_sms() * 4, solver::kWarpsPerBlock * 32, 0, st>>>(
                 e->dp.sreq_own + r0, e->dp.sreq_enemy + r0, e->dp.sreq_exact + r0, e->dp.sres_move + r0, e->dp.sres_score + r0,
-                e->dp.solve_count + g * 64);
+                e->dp.solve_count + g * 64, e->dp.solver_tt + (size_t)g * e->solver_tt_words_per_group);
             RZ_LAUNCH_CHECK();
             e->mcts_launches++;
         }
@@ -915,6 +919,10 @@ int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net, int device, rz_engin
     if (!rc) rc = dev_alloc(e, (void**)&p.sreq_exact, SR, true);
     if (!rc) rc = dev_alloc(e, (void**)&p.sres_move, SR, true);
     if (!rc) rc = dev_alloc(e, (void**)&p.sres_score, SR, true);
+    p.solver_tt = nullptr;
+    e->solver_tt_words_per_group = (size_t)num_sms() * 4 * solver::kWarpsPerBlock * solver::kTtEntries * solver::kTtWordsPerEntry;
+    if (!rc && (c.solver_turn > 0 || c.solver_sim_turn > 0))
+        rc = dev_alloc(e, (void**)&p.solver_tt, e->solver_tt_words_per_group * 2 * sizeof(u64), true);
     if (!rc && cudaMallocHost((void**)&e->h_status, sizeof(Status)) != cudaSuccess) { set_error("cudaMallocHost failed"); rc = RZ_ENOMEM; }
     if (!rc && cudaMallocHost((void**)&e->h_flags, G * 2) != cudaSuccess) { set_error("cudaMallocHost failed"); rc = RZ_ENOMEM; }
     for (int i = 0; i < 48 && !rc; ++i)

@@ -10,12 +10,13 @@ constexpr int kWarpsPerBlock = 4;
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) solve_kernel(const u64* __restrict__ own, const u64* __restrict__ enemy,
                                                                     const uint8_t* __restrict__ exactly, int8_t* __restrict__ move,
-                                                                    int8_t* __restrict__ score, size_t n) {
+                                                                    int8_t* __restrict__ score, size_t n, u64* tt_base) {
     __shared__ int8_t vals[kWarpsPerBlock][kMaxTasks];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const TT tt{tt_base ? tt_base + ((size_t)blockIdx.x * kWarpsPerBlock + w) * kTtEntries * kTtWordsPerEntry : nullptr};
     for (size_t i = (size_t)blockIdx.x * kWarpsPerBlock + w; i < n; i += (size_t)gridDim.x * kWarpsPerBlock) {
         int mv, sc;
-        solve_warp(own[i], enemy[i], exactly[i] != 0, vals[w], lane, mv, sc);
+        solve_warp(own[i], enemy[i], exactly[i] != 0, vals[w], lane, mv, sc, tt);
         if (lane == 0) { move[i] = (int8_t)mv; score[i] = (int8_t)(mv < 0 ? 0 : sc); }
         __syncwarp();
     }
@@ -32,9 +33,20 @@ int rz_solve_dev(const uint64_t* own, const uint64_t* enemy, const uint8_t* exac
     RZ_REQUIRE(n == 0 || (own && enemy && exactly && move && score), "rz_solve_dev: null pointer");
     if (n == 0) return RZ_OK;
     size_t blocks = (n + solver::kWarpsPerBlock - 1) / solver::kWarpsPerBlock;
-    const size_t cap = (size_t)num_sms() * 16;
+    const size_t cap = (size_t)num_sms() * 4;
     if (blocks > cap) blocks = cap;
-    solver::solve_kernel<<<(unsigned)blocks, solver::kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(own, enemy, exactly, move, score, n);
+    // per-warp transposition tables (kept for the life of the process; entries are position facts and never go stale)
+    static u64* tt_base = nullptr;
+    static size_t tt_warps = 0;
+    if (tt_warps < cap * solver::kWarpsPerBlock) {
+        if (tt_base) cudaFree(tt_base);
+        tt_base = nullptr; tt_warps = 0;
+        const size_t bytes = cap * solver::kWarpsPerBlock * (size_t)solver::kTtEntries * solver::kTtWordsPerEntry * sizeof(u64);
+        RZ_CUDA_TRY(cudaMalloc((void**)&tt_base, bytes));
+        RZ_CUDA_TRY(cudaMemsetAsync(tt_base, 0, bytes, (cudaStream_t)stream));
+        tt_warps = cap * solver::kWarpsPerBlock;
+    }
+    solver::solve_kernel<<<(unsigned)blocks, solver::kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(own, enemy, exactly, move, score, n, tt_base);
     RZ_LAUNCH_CHECK();
     return RZ_OK;
 }

@@ -19,13 +19,52 @@ constexpr int kSolverMaxEmpties = 12;
 constexpr int kMaxTasks = 256;   // > 12 * 11 second-ply positions
 constexpr int kMaxDepth = 24;
 
+// Transposition table of the WLD mode (the reference's `cache` dict, reversi_solver_cython.pyx:83-90,102): one
+// direct-mapped table per warp in global memory, shared by its 32 lanes without locks.  An entry is three words
+// (own ^ tag, enemy ^ tag, tag) with tag = 48-bit hash of the position | score byte, so a torn or foreign entry fails
+// validation instead of returning a wrong score.  A position's WLD value is a pure function of the position, so
+// entries stay valid across requests and never need clearing.  Without it a 10-empties WLD solve walks millions of
+// nodes (the reference is only fast because of its cache).
+constexpr uint32_t kTtEntries = 1u << 13;           // per warp
+constexpr int kTtWordsPerEntry = 4;                 // 32 B
+constexpr int kTtMinEmpties = 4;                    // smaller subtrees are cheaper to recompute than to look up
+struct TT {
+    u64* base;  // nullptr: no table
+    __device__ __forceinline__ static u64 mix(u64 own, u64 enemy) {
+        u64 h = own * 0x9E3779B97F4A7C15ULL ^ (enemy + 0x632BE59BD9B4E019ULL) * 0xC2B2AE3D27D4EB4FULL;
+        h ^= h >> 31; h *= 0xD6E8FEB86659FD93ULL; h ^= h >> 29;
+        return h;
+    }
+    __device__ __forceinline__ bool probe(u64 own, u64 enemy, int& score) const {
+        if (!base) return false;
+        const u64 h = mix(own, enemy);
+        const u64* e = base + (size_t)(h & (kTtEntries - 1)) * kTtWordsPerEntry;
+        const u64 w0 = e[0], w1 = e[1], w2 = e[2];
+        if ((w0 ^ w2) != own || (w1 ^ w2) != enemy || (w2 >> 16) != (h >> 16) || ((w2 >> 8) & 0xFF) != 0x5A) return false;
+        score = (int)(int8_t)(w2 & 0xFF);
+        return true;
+    }
+    __device__ __forceinline__ void store(u64 own, u64 enemy, int score) const {
+        if (!base) return;
+        const u64 h = mix(own, enemy);
+        u64* e = base + (size_t)(h & (kTtEntries - 1)) * kTtWordsPerEntry;
+        const u64 w2 = (h & ~0xFFFFULL) | (0x5AULL << 8) | (u64)(uint8_t)(int8_t)score;
+        e[0] = own ^ w2; e[1] = enemy ^ w2; e[2] = w2;
+    }
+};
+
 struct Frame {
     u64 own, enemy, moves;
     int8_t best, alpha, beta, sign;  // sign: factor applied to this frame's value when it returns to its parent
 };
 
 // value of the position for the side to move (`own`, which has at least one legal move)
-__device__ inline int solve_subtree(u64 own, u64 enemy, bool exactly) {
+__device__ inline int solve_subtree(u64 own, u64 enemy, bool exactly, const TT& tt) {
+    const bool cached = !exactly && tt.base != nullptr;  // exact mode prunes (alpha-beta), its node values are bounds: not cached
+    if (cached && 64 - popc64(own | enemy) >= kTtMinEmpties) {
+        int sc;
+        if (tt.probe(own, enemy, sc)) return sc;
+    }
     Frame f[kMaxDepth];
     int d = 0;
     f[0].own = own; f[0].enemy = enemy; f[0].moves = find_correct_moves(own, enemy);
@@ -33,6 +72,7 @@ __device__ inline int solve_subtree(u64 own, u64 enemy, bool exactly) {
     while (true) {
         Frame& F = f[d];
         if (F.moves == 0 || (!exactly && F.best > 0) || (exactly && F.best >= F.beta)) {
+            if (cached && 64 - popc64(F.own | F.enemy) >= kTtMinEmpties) tt.store(F.own, F.enemy, F.best);
             if (d == 0) return F.best;
             const int v = F.best * F.sign;
             --d;
@@ -45,6 +85,14 @@ __device__ inline int solve_subtree(u64 own, u64 enemy, bool exactly) {
         const u64 own2 = (F.own ^ fl) | (1ULL << a), en2 = F.enemy ^ fl;
         const int lo = F.best > F.alpha ? F.best : F.alpha;  // alpha-beta lower bound at this node (exact mode)
         u64 m = find_correct_moves(en2, own2);
+        if (cached && 64 - popc64(own2 | en2) >= kTtMinEmpties) {  // child already solved?
+            int sc;
+            if (m ? tt.probe(en2, own2, sc) : (find_correct_moves(own2, en2) != 0 && tt.probe(own2, en2, sc))) {
+                const int v = m ? -sc : sc;
+                if (F.best < v) F.best = (int8_t)v;
+                continue;
+            }
+        }
         if (m) {  // opponent to move
             if (d + 1 >= kMaxDepth) return F.best;  // cannot happen for <= kSolverMaxEmpties empties
             Frame& C = f[++d];
@@ -75,7 +123,7 @@ __device__ __forceinline__ bool after_move(u64 own, u64 enemy, int a, u64& nown,
 
 // Called by a full warp with identical arguments; `vals` is a per-warp scratch array of kMaxTasks int8 in shared memory.
 // Returns (move, score) in all lanes; move = -1: no legal move or position refused.
-__device__ inline void solve_warp(u64 own, u64 enemy, bool exactly, int8_t* vals, int lane, int& move_out, int& score_out) {
+__device__ inline void solve_warp(u64 own, u64 enemy, bool exactly, int8_t* vals, int lane, int& move_out, int& score_out, const TT& tt) {
     move_out = -1; score_out = -100;
     const u64 legal = find_correct_moves(own, enemy);
     if (!legal || 64 - popc64(own | enemy) > kSolverMaxEmpties) return;
@@ -87,7 +135,7 @@ __device__ inline void solve_warp(u64 own, u64 enemy, bool exactly, int8_t* vals
         for (u64 m2 = find_correct_moves(o1, e1); m2; m2 &= m2 - 1) {
             u64 o2, e2; int s2, sc2;
             if (after_move(o1, e1, ctz64(m2), o2, e2, s2, sc2)) continue;
-            if ((t & 31) == lane && t < kMaxTasks) vals[t] = (int8_t)solve_subtree(o2, e2, exactly);
+            if ((t & 31) == lane && t < kMaxTasks) vals[t] = (int8_t)solve_subtree(o2, e2, exactly, tt);
             ++t;
         }
     }
