@@ -127,7 +127,26 @@ __device__ inline void solve_warp(u64 own, u64 enemy, bool exactly, int8_t* vals
     move_out = -1; score_out = -100;
     const u64 legal = find_correct_moves(own, enemy);
     if (!legal || 64 - popc64(own | enemy) > kSolverMaxEmpties) return;
-    // pass 1: every lane enumerates the grand-child tasks identically and solves those with index == lane (mod 32)
+    if (!exactly) {
+        // WLD mode: the reference's early stop makes the search lazy -- it never looks at the root moves behind the first
+        // winning one, and with the transposition table the whole tree is a few thousand nodes -- so evaluating all
+        // second-ply subtrees in parallel does far MORE work than the sequential walk.  One lane walks the tree in the
+        // reference's order (the request-level parallelism comes from the thousands of warps in flight).
+        int best = -100, best_move = -1;
+        if (lane == 0) {
+            for (u64 m1 = legal; m1; m1 &= m1 - 1) {
+                if (best > 0) break;                              // reversi_solver_cython.pyx:99 at the root
+                const int a1 = ctz64(m1);
+                u64 o1, e1; int s1, sc1;
+                const int v1 = after_move(own, enemy, a1, o1, e1, s1, sc1) ? sc1 : s1 * solve_subtree(o1, e1, false, tt);
+                if (best < v1) { best = v1; best_move = a1; }
+            }
+        }
+        move_out = __shfl_sync(0xffffffffu, best_move, 0);
+        score_out = __shfl_sync(0xffffffffu, best, 0);
+        return;
+    }
+    // exact mode -- pass 1: every lane enumerates the grand-child tasks identically and solves those with index == lane (mod 32)
     int t = 0;
     for (u64 m1 = legal; m1; m1 &= m1 - 1) {
         u64 o1, e1; int s1, sc1;
