@@ -57,6 +57,22 @@ struct Frame {
     u64 own, enemy, moves;
     int8_t best, alpha, beta, sign;  // sign: factor applied to this frame's value when it returns to its parent
 };
+constexpr int kOrderMinEmpties = 5;
+
+// exact mode only: next move to try = the remaining move that leaves the opponent the fewest replies ("fastest first").
+// Inner nodes of the exact search only contribute their VALUE (the first-best-move rule of the reference is resolved at
+// the two top plies, which keep the ascending order), and alpha-beta with any move order returns the same value.
+__device__ __forceinline__ int pick_move(u64 own, u64 enemy, u64 moves, bool ordered) {
+    if (!ordered || (moves & (moves - 1)) == 0) return ctz64(moves);
+    int best_a = -1, best_mob = 99;
+    for (u64 m = moves; m; m &= m - 1) {
+        const int a = ctz64(m);
+        const u64 fl = calc_flip(a, own, enemy);
+        const int mob = popc64(find_correct_moves(enemy ^ fl, (own ^ fl) | (1ULL << a)));
+        if (mob < best_mob) { best_mob = mob; best_a = a; }
+    }
+    return best_a;
+}
 
 // value of the position for the side to move (`own`, which has at least one legal move)
 __device__ inline int solve_subtree(u64 own, u64 enemy, bool exactly, const TT& tt) {
@@ -79,8 +95,8 @@ __device__ inline int solve_subtree(u64 own, u64 enemy, bool exactly, const TT& 
             if (f[d].best < v) f[d].best = (int8_t)v;
             continue;
         }
-        const int a = ctz64(F.moves);
-        F.moves &= F.moves - 1;
+        const int a = pick_move(F.own, F.enemy, F.moves, exactly && 64 - popc64(F.own | F.enemy) >= kOrderMinEmpties);
+        F.moves &= ~(1ULL << a);
         const u64 fl = calc_flip(a, F.own, F.enemy);
         const u64 own2 = (F.own ^ fl) | (1ULL << a), en2 = F.enemy ^ fl;
         const int lo = F.best > F.alpha ? F.best : F.alpha;  // alpha-beta lower bound at this node (exact mode)
