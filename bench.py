@@ -83,11 +83,12 @@ def expansions_per_game():
     profiles/; the fallback is the value probed on the reference (21 256 at sim = 400)."""
     sims = PLAY_KW["simulation_num_per_move"]
     try:
-        with open(os.path.join(ROOT, "profiles", "full_games_solver_on.json" if PLAY_KW.get("use_solver_turn") else "full_games.json")) as f:
+        name = "full_games_solver_on.json" if PLAY_KW.get("use_solver_turn") else "full_games.json"
+        with open(os.path.join(ROOT, "profiles", name)) as f:
             d = json.load(f)
         if "sims=%d " % sims in d["workload"]:
-            return float(d["expansions_per_game"]), "measured: profiles/full_games.json (%d complete games)" % d["games"]
-        return float(d["expansions_per_game"]) * sims / 400.0, "ESTIMATE: profiles/full_games.json (sims=400) scaled by sims/400"
+            return float(d["expansions_per_game"]), "measured: profiles/%s (%d complete games)" % (name, d["games"])
+        return float(d["expansions_per_game"]) * sims / 400.0, "ESTIMATE: profiles/%s (sims=400) scaled by sims/400" % name
     except Exception:
         return 21256.0 * sims / 400.0, "fallback: reference probe at sim=400 (SURVEY 3.1), scaled by sims/400"
 
@@ -277,7 +278,8 @@ def main():
     for k, v in PLAY_KW.items():
         setattr(cfg.play, k, v)
     cfg.play.schedule_of_simulation_num_per_move = [(0, PLAY_KW["simulation_num_per_move"])]
-    cfg.play.use_solver_turn = cfg.play.use_solver_turn_in_simulation = 0
+    cfg.play.use_solver_turn = PLAY_KW.get("use_solver_turn", 0)
+    cfg.play.use_solver_turn_in_simulation = PLAY_KW.get("use_solver_turn_in_simulation", 0)
     cfg.play_data.nb_game_in_file = 64
     cfg.play_data.enable_ggf_data = False
     cfg.b200.games_per_gpu = args.games

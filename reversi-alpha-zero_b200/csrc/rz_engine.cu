@@ -30,21 +30,23 @@
 
 namespace rz {
 namespace solver {
-constexpr int kWarpsPerBlock = 4;
-// the engine's per-wave solver batch: the request count is produced on the device by the tick kernel
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) solve_counted_kernel(const u64* __restrict__ own, const u64* __restrict__ enemy,
-                                                                            const uint8_t* __restrict__ exactly, int8_t* __restrict__ move,
-                                                                            int8_t* __restrict__ score, const uint32_t* __restrict__ count,
-                                                                            u64* tt_base) {
-    __shared__ int8_t vals[kWarpsPerBlock][kMaxTasks];
-    const uint32_t n = *count;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const TT tt{tt_base + ((size_t)blockIdx.x * kWarpsPerBlock + w) * kTtEntries * kTtWordsPerEntry};
-    for (uint32_t i = blockIdx.x * kWarpsPerBlock + w; i < n; i += gridDim.x * kWarpsPerBlock) {
-        int mv, sc;
-        solve_warp(own[i], enemy[i], exactly[i] != 0, vals[w], lane, mv, sc, tt);
-        if (lane == 0) { move[i] = (int8_t)mv; score[i] = (int8_t)(mv < 0 ? 0 : sc); }
-        __syncwarp();
+constexpr int kBlockThreads = 128;
+// The engine's solver step: advance every unfinished request of a slot group for at most `budget_ns`, then queue what is
+// still unfinished for the group's next wave.  `active` holds request-context indices: the unfinished ones of the last
+// wave followed by those the tick kernel just added.  One CTA per SM, so all of them are resident beside the other
+// group's network kernel and the step costs at most about `budget_ns` of stream time.
+__global__ void __launch_bounds__(kBlockThreads) solve_active_kernel(SolveCtx* __restrict__ ctx, const uint32_t* __restrict__ active,
+                                                                     const uint32_t* __restrict__ n_active, uint32_t* __restrict__ next,
+                                                                     uint32_t* __restrict__ n_next, u64* tt_base, long long budget_ns) {
+    const uint32_t n = *n_active;
+    if (n == 0) return;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, total = gridDim.x * blockDim.x, n_warps = total >> 5;
+    const long long deadline = global_ns() + budget_ns;
+    const TT tt{tt_base + (size_t)tid * kTtEntries * kTtWordsPerEntry};
+    // request r -> lane r / n_warps of warp r % n_warps: spreads a short list over all warps (few divergent lanes per warp)
+    for (uint32_t r = (tid & 31u) * n_warps + (tid >> 5); r < n; r += total) {
+        const uint32_t idx = active[r];
+        if (!solve_advance(ctx + idx, tt, deadline)) next[atomicAdd(n_next, 1u)] = idx;
     }
 }
 }  // namespace solver
@@ -93,7 +95,9 @@ struct Descent {
     u64 leaf_own, leaf_enemy;
     uint32_t leaf_index;     // row in the evaluation batch
     uint8_t next_player, status, dihedral, path_len;
-    uint8_t leaf_mover_is_root, pad[3];
+    uint8_t leaf_mover_is_root;
+    uint8_t kept;            // 1: the network result of this leaf was copied to keep_policy / keep_value
+    uint8_t pad[2];
     uint32_t path[kMaxPath];  // edge index within the slot's arena | (mover_is_root << 31)
 };
 
@@ -148,14 +152,14 @@ struct DevPtrs {
     u64* batch_enemy;
     float* policy;         // [G*K][64]
     float* value;          // [G*K]
-    // endgame solver requests of the current wave (rows [slot0 * (K + 1), ...) per group) and their results
-    uint32_t* solve_count; // [2 groups] (64 words apart)
-    u64* sreq_own;
-    u64* sreq_enemy;
-    uint8_t* sreq_exact;
-    int8_t* sres_move;
-    int8_t* sres_score;
-    u64* solver_tt;        // per-warp transposition tables of the solver kernel, one set per slot group
+    // endgame solver: one resumable request context per descent (+ one per slot for the exact root solve), the lists of
+    // unfinished requests (per group, double-buffered by wave parity) and the network results a waiting slot has to keep
+    solver::SolveCtx* sctx;  // [G][K + 1]
+    uint32_t* sactive;       // [2 groups][2 parities][G * (K + 1)]
+    uint32_t* solve_count;   // [2 groups][2 parities] (64 words apart)
+    float* keep_policy;      // [G*K][64]
+    float* keep_value;       // [G*K]
+    u64* solver_tt;          // per-lane transposition tables of the solver kernel, one set per slot group
 };
 
 __device__ __forceinline__ uint32_t hash_key(u64 own, u64 enemy, uint32_t kpid) {
@@ -709,6 +713,8 @@ struct rz_engine {
     int n_groups;
     int group_slot0[3];
     size_t solver_tt_words_per_group;
+    int solve_parity[2];      // per group: which of its two unfinished-solve lists the next wave reads
+    long long solver_budget_ns;  // time the solver step may take per wave and group (RZ_SOLVER_BUDGET_US)
     int tick_impl;            // 0 = warp-per-game kernel (default), 1 = thread-per-slot cross-check (RZ_TICK_IMPL=thread)
     void* arena[32];
     int n_arena;
@@ -781,20 +787,24 @@ static int launch_wave(rz_engine* e) {
         const size_t rows = (size_t)(s1 - s0) * c.K;
         if (timed) RZ_CUDA_TRY(cudaEventRecord(ev[0], st));
         for (int net = 0; net <= c.two_nets; ++net) RZ_CUDA_TRY(cudaMemsetAsync(e->dp.batch_count + (net * 2 + g) * 64, 0, sizeof(uint32_t), st));
-        RZ_CUDA_TRY(cudaMemsetAsync(e->dp.solve_count + g * 64, 0, sizeof(uint32_t), st));
+        const bool solving = c.solver_turn > 0 || c.solver_sim_turn > 0;
+        const int par = e->solve_parity[g];  // the unfinished-solve list this wave's tick appends to
+        if (solving) RZ_CUDA_TRY(cudaMemsetAsync(e->dp.solve_count + (g * 2 + (1 - par)) * 64, 0, sizeof(uint32_t), st));
         if (e->tick_impl == 1)
             tick_kernel<<<(s1 - s0 + kTickThreads - 1) / kTickThreads, kTickThreads, 0, st>>>(c, e->dp, s0, s1, g);
         else
-            tick_warp_kernel<<<(s1 - s0 + 1) / 2, kWarpTickThreads, 0, st>>>(c, e->dp, s0, s1, g);
+            tick_warp_kernel<<<(s1 - s0 + 1) / 2, kWarpTickThreads, 0, st>>>(c, e->dp, s0, s1, g, par);
         RZ_LAUNCH_CHECK();
         e->mcts_launches++;
-        if (c.solver_turn > 0 || c.solver_sim_turn > 0) {  // this wave's solver requests: runs underneath the other group's tower
-            const size_t r0 = (size_t)s0 * (c.K + 1);
-            solver::solve_counted_kernel<<<num_sms() * 4, solver::kWarpsPerBlock * 32, 0, st>>>(
-                e->dp.sreq_own + r0, e->dp.sreq_enemy + r0, e->dp.sreq_exact + r0, e->dp.sres_move + r0, e->dp.sres_score + r0,
-                e->dp.solve_count + g * 64, e->dp.solver_tt + (size_t)g * e->solver_tt_words_per_group);
+        if (solving) {  // advance the group's unfinished solves for a bounded time (underneath the other group's tower)
+            const size_t list = (size_t)c.G * (c.K + 1);
+            solver::solve_active_kernel<<<num_sms(), solver::kBlockThreads, 0, st>>>(
+                e->dp.sctx, e->dp.sactive + (g * 2 + par) * list, e->dp.solve_count + (g * 2 + par) * 64,
+                e->dp.sactive + (g * 2 + (1 - par)) * list, e->dp.solve_count + (g * 2 + (1 - par)) * 64,
+                e->dp.solver_tt + (size_t)g * e->solver_tt_words_per_group, e->solver_budget_ns);
             RZ_LAUNCH_CHECK();
             e->mcts_launches++;
+            e->solve_parity[g] = 1 - par;
         }
         if (timed) RZ_CUDA_TRY(cudaEventRecord(ev[1], st));
         for (int net = 0; net <= c.two_nets; ++net) {
@@ -912,17 +922,25 @@ int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net, int device, rz_engin
     if (!rc) rc = dev_alloc(e, (void**)&p.batch_enemy, (B + 2) * sizeof(u64), true);
     if (!rc) rc = dev_alloc(e, (void**)&p.policy, (B + 2) * 64 * sizeof(float), true);
     if (!rc) rc = dev_alloc(e, (void**)&p.value, (B + 2) * sizeof(float), true);
-    const size_t SR = G * (c.K + 1) + 8;
+    const bool solving = c.solver_turn > 0 || c.solver_sim_turn > 0;
+    const size_t SR = G * (c.K + 1);
     if (!rc) rc = dev_alloc(e, (void**)&p.solve_count, 1024, true);
-    if (!rc) rc = dev_alloc(e, (void**)&p.sreq_own, SR * sizeof(u64), true);
-    if (!rc) rc = dev_alloc(e, (void**)&p.sreq_enemy, SR * sizeof(u64), true);
-    if (!rc) rc = dev_alloc(e, (void**)&p.sreq_exact, SR, true);
-    if (!rc) rc = dev_alloc(e, (void**)&p.sres_move, SR, true);
-    if (!rc) rc = dev_alloc(e, (void**)&p.sres_score, SR, true);
-    p.solver_tt = nullptr;
-    e->solver_tt_words_per_group = (size_t)num_sms() * 4 * solver::kWarpsPerBlock * solver::kTtEntries * solver::kTtWordsPerEntry;
-    if (!rc && (c.solver_turn > 0 || c.solver_sim_turn > 0))
-        rc = dev_alloc(e, (void**)&p.solver_tt, e->solver_tt_words_per_group * 2 * sizeof(u64), true);
+    p.sctx = nullptr; p.sactive = nullptr; p.keep_policy = nullptr; p.keep_value = nullptr; p.solver_tt = nullptr;
+    e->solve_parity[0] = e->solve_parity[1] = 0;
+    {
+        const char* b = getenv("RZ_SOLVER_BUDGET_US");
+        const long long us = b ? atoll(b) : 4000;
+        e->solver_budget_ns = (us > 0 ? us : 4000) * 1000LL;
+    }
+    // one transposition table per lane of the solver step's grid (one CTA per SM), one set per slot group
+    e->solver_tt_words_per_group = (size_t)num_sms() * solver::kBlockThreads * solver::kTtEntries * solver::kTtWordsPerEntry;
+    if (solving) {
+        if (!rc) rc = dev_alloc(e, (void**)&p.sctx, SR * sizeof(solver::SolveCtx), true);
+        if (!rc) rc = dev_alloc(e, (void**)&p.sactive, 4 * SR * sizeof(uint32_t), true);
+        if (!rc) rc = dev_alloc(e, (void**)&p.keep_policy, G * c.K * 64 * sizeof(float), true);
+        if (!rc) rc = dev_alloc(e, (void**)&p.keep_value, G * c.K * sizeof(float), true);
+        if (!rc) rc = dev_alloc(e, (void**)&p.solver_tt, e->solver_tt_words_per_group * 2 * sizeof(u64), true);
+    }
     if (!rc && cudaMallocHost((void**)&e->h_status, sizeof(Status)) != cudaSuccess) { set_error("cudaMallocHost failed"); rc = RZ_ENOMEM; }
     if (!rc && cudaMallocHost((void**)&e->h_flags, G * 2) != cudaSuccess) { set_error("cudaMallocHost failed"); rc = RZ_ENOMEM; }
     for (int i = 0; i < 48 && !rc; ++i)

@@ -278,7 +278,8 @@ struct WCtx {
             sl.n_solves++;
             bool applied = false;
             if (ni >= 0) {
-                if (lane == 0) nodes[ni].pad = wld_encode(p.sres_move[D.leaf_index], p.sres_score[D.leaf_index]);
+                const solver::SolveCtx& sc = p.sctx[(size_t)s * (c.K + 1) + di];
+                if (lane == 0) nodes[ni].pad = wld_encode(sc.move, sc.score);
                 __syncwarp();
                 applied = apply_wld(ni, D.path, D.path_len, D.leaf_mover_is_root != 0);
             }
@@ -288,7 +289,7 @@ struct WCtx {
         }
         if (ni >= 0) {
             const Node nd = nodes[ni];
-            const float* pol = p.policy + (size_t)D.leaf_index * 64;
+            const float* pol = D.kept ? p.keep_policy + ((size_t)s * c.K + di) * 64 : p.policy + (size_t)D.leaf_index * 64;
             const float a_lo = ((nd.legal >> lane) & 1ULL) ? pol[dihedral_square(lane, t)] : 0.f;
             const float a_hi = ((nd.legal >> (lane + 32)) & 1ULL) ? pol[dihedral_square(lane + 32, t)] : 0.f;
             // numpy float32 sum order: 8 running column sums over the rows, then a fixed tree
@@ -314,8 +315,9 @@ struct WCtx {
             if (lane == 0) nodes[ni].exp = nd.exp | (uint8_t)(1u << (pid - 1));
             __syncwarp();
         }
-        const float v = p.value[D.leaf_index];
+        const float v = D.kept ? p.keep_value[(size_t)s * c.K + di] : p.value[D.leaf_index];
         backup(D.path, D.path_len, D.leaf_mover_is_root ? v : -v);
+        if (D.kept && lane == 0) desc[di].kept = 0;
         dstat[di] = D_FREE;
     }
 
@@ -387,7 +389,8 @@ struct WCtx {
     __device__ void consume_root_solve() {
         const u64 own = sl.root_own, enemy = sl.root_enemy;
         const int pid = sl.root_pid;
-        const int mv = p.sres_move[sl.root_solve_index], sc = p.sres_score[sl.root_solve_index];
+        const solver::SolveCtx& rc = p.sctx[(size_t)s * (c.K + 1) + c.K];
+        const int mv = rc.move, sc = rc.score;
         sl.n_solves++;
         if (mv < 0) { begin_search(own, enemy, pid); return; }  // refused (the reference: timeout) -> search as usual
         const uint32_t kp = kpid_of(pid);
@@ -586,7 +589,7 @@ struct WCtx {
 constexpr int kWarpTickThreads = 64;  // 2 game slots per CTA: 64 x 124 registers fit beside a resident tower CTA (320 x 168)
 
 __global__ void __launch_bounds__(kWarpTickThreads) tick_warp_kernel(const DevCfg c, const DevPtrs p, const int slot0, const int slot_end,
-                                                                     const int group) {
+                                                                     const int group, const int parity) {
     const int lane = threadIdx.x & 31;
     const int s = slot0 + (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (s >= slot_end) return;  // whole warps only
@@ -595,6 +598,29 @@ __global__ void __launch_bounds__(kWarpTickThreads) tick_warp_kernel(const DevCf
     Slot& sl = x.sl;
     if (sl.phase == PH_IDLE) return;
     if (sl.phase == PH_SEARCH) {  // 1. consume the previous wave's evaluations in request order
+        // ... once every endgame solve the slot asked for is finished: a solve may take several waves, and until then the
+        // slot does nothing (the search result cannot depend on how long a solve took).  Network results that arrived in
+        // the meantime are copied out of the batch buffers, which the next wave overwrites.
+        bool ready = true;
+        for (int j = 0; j < (int)sl.n_pending; ++j) {
+            const int di = sl.pending[j];
+            if (x.desc[di].dihedral == kSolveMarker && !p.sctx[(size_t)s * (c.K + 1) + di].done) ready = false;
+        }
+        if (!ready) {
+            for (int j = 0; j < (int)sl.n_pending; ++j) {
+                const int di = sl.pending[j];
+                Descent& d = x.desc[di];
+                if (d.dihedral == kSolveMarker || d.kept) continue;
+                float* kp = p.keep_policy + ((size_t)s * c.K + di) * 64;
+                const float* src = p.policy + (size_t)d.leaf_index * 64;
+                kp[lane] = src[lane]; kp[lane + 32] = src[lane + 32];
+                if (lane == 0) { p.keep_value[(size_t)s * c.K + di] = p.value[d.leaf_index]; }
+                __syncwarp();
+                if (lane == 0) d.kept = 1;
+            }
+            __syncwarp();
+            return;
+        }
         const uint32_t consumed = sl.n_pending;
         uint32_t nn_consumed = 0;
         for (int j = 0; j < (int)consumed; ++j) {
@@ -604,6 +630,7 @@ __global__ void __launch_bounds__(kWarpTickThreads) tick_warp_kernel(const DevCf
         sl.n_pending = 0;
         if (nn_consumed && lane == 0) atomicAdd(&p.status->expansions, (unsigned long long)nn_consumed);
     } else if (sl.phase == PH_SOLVE && !sl.root_req) {
+        if (!p.sctx[(size_t)s * (c.K + 1) + c.K].done) return;  // the exact root solve needs more waves
         x.consume_root_solve();
     }
     for (int guard = 0; guard < 100000; ++guard) {  // 2. advance the state machine until the network is needed
@@ -632,27 +659,32 @@ __global__ void __launch_bounds__(kWarpTickThreads) tick_warp_kernel(const DevCf
     const uint32_t n_nn = __popc(nn_mask), n_sv = __popc(sv_mask) + root_req;
     const uint32_t net = c.two_nets ? sl.cur_net : 0u;  // evaluation matches: every search is evaluated by the mover's network
     uint32_t base = 0, sbase = 0;
+    uint32_t* s_count = p.solve_count + (group * 2 + parity) * 64;
+    uint32_t* s_list = p.sactive + (size_t)(group * 2 + parity) * c.G * (c.K + 1);
     if (lane == 0 && n_nn > 0) base = atomicAdd(p.batch_count + (net * 2 + group) * 64, n_nn);
-    if (lane == 0 && n_sv > 0) sbase = atomicAdd(p.solve_count + group * 64, n_sv);
+    if (lane == 0 && n_sv > 0) sbase = atomicAdd(s_count, n_sv);
     base = __shfl_sync(0xffffffffu, base, 0);
     sbase = __shfl_sync(0xffffffffu, sbase, 0);
-    if (root_req) { sl.root_solve_index = (uint32_t)slot0 * (uint32_t)(c.K + 1) + sbase + (n_sv - 1); sl.root_req = 0; }
+    if (root_req) sl.root_req = 0;
     x.write_back();
     const uint32_t below = (1u << lane) - 1u;
     if (mine && !is_solve) {
         Descent& d = x.desc[sl.pending[lane]];
         const uint32_t at = net * (uint32_t)c.G * (uint32_t)c.K + (uint32_t)slot0 * (uint32_t)c.K + base + __popc(nn_mask & below);
         d.leaf_index = at;
+        d.kept = 0;
         p.batch_own[at] = dihedral(d.leaf_own, d.dihedral);
         p.batch_enemy[at] = dihedral(d.leaf_enemy, d.dihedral);
-    } else if (is_solve) {
-        Descent& d = x.desc[sl.pending[lane]];
-        const uint32_t at = (uint32_t)slot0 * (uint32_t)(c.K + 1) + sbase + __popc(sv_mask & below);
-        d.leaf_index = at;
-        p.sreq_own[at] = d.leaf_own; p.sreq_enemy[at] = d.leaf_enemy; p.sreq_exact[at] = 0;
+    } else if (is_solve) {  // WLD solve of a simulation's position: context of this descent
+        const int di = sl.pending[lane];
+        const Descent& d = x.desc[di];
+        const uint32_t idx = (uint32_t)s * (uint32_t)(c.K + 1) + (uint32_t)di;
+        solver::ctx_init(p.sctx + idx, d.leaf_own, d.leaf_enemy, 0);
+        s_list[sbase + __popc(sv_mask & below)] = idx;
     }
-    if (root_req && lane == 0) {
-        const uint32_t at = sl.root_solve_index;
-        p.sreq_own[at] = sl.root_own; p.sreq_enemy[at] = sl.root_enemy; p.sreq_exact[at] = 1;
+    if (root_req && lane == 0) {  // exact solve of the root: the slot's own context
+        const uint32_t idx = (uint32_t)s * (uint32_t)(c.K + 1) + (uint32_t)c.K;
+        solver::ctx_init(p.sctx + idx, sl.root_own, sl.root_enemy, 1);
+        s_list[sbase + (n_sv - 1)] = idx;
     }
 }

@@ -6,19 +6,26 @@
 namespace rz {
 namespace solver {
 
-constexpr int kWarpsPerBlock = 4;
+constexpr int kBlockThreads = 128;
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) solve_kernel(const u64* __restrict__ own, const u64* __restrict__ enemy,
-                                                                    const uint8_t* __restrict__ exactly, int8_t* __restrict__ move,
-                                                                    int8_t* __restrict__ score, size_t n, u64* tt_base) {
-    __shared__ int8_t vals[kWarpsPerBlock][kMaxTasks];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const TT tt{tt_base ? tt_base + ((size_t)blockIdx.x * kWarpsPerBlock + w) * kTtEntries * kTtWordsPerEntry : nullptr};
-    for (size_t i = (size_t)blockIdx.x * kWarpsPerBlock + w; i < n; i += (size_t)gridDim.x * kWarpsPerBlock) {
-        int mv, sc;
-        solve_warp(own[i], enemy[i], exactly[i] != 0, vals[w], lane, mv, sc, tt);
-        if (lane == 0) { move[i] = (int8_t)mv; score[i] = (int8_t)(mv < 0 ? 0 : sc); }
-        __syncwarp();
+// request r of a launch is served by lane (r / n_warps) of warp (r % n_warps): a batch smaller than the grid is spread over
+// all warps, so each warp carries as few divergent lanes as possible
+__device__ __forceinline__ uint32_t spread_index(uint32_t tid, uint32_t total) {
+    const uint32_t n_warps = total >> 5;
+    return (tid & 31u) * n_warps + (tid >> 5);
+}
+
+__global__ void __launch_bounds__(kBlockThreads) solve_kernel(const u64* __restrict__ own, const u64* __restrict__ enemy,
+                                                              const uint8_t* __restrict__ exactly, int8_t* __restrict__ move,
+                                                              int8_t* __restrict__ score, size_t n, SolveCtx* scratch, u64* tt_base) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, total = gridDim.x * blockDim.x;
+    const TT tt{tt_base + (size_t)tid * kTtEntries * kTtWordsPerEntry};
+    SolveCtx* c = scratch + tid;
+    for (size_t i = spread_index(tid, total); i < n; i += total) {
+        ctx_init(c, own[i], enemy[i], exactly[i] != 0);
+        solve_advance(c, tt, 0);
+        move[i] = c->move;
+        score[i] = (int8_t)(c->move < 0 ? 0 : c->score);
     }
 }
 
@@ -32,21 +39,19 @@ extern "C" {
 int rz_solve_dev(const uint64_t* own, const uint64_t* enemy, const uint8_t* exactly, int8_t* move, int8_t* score, size_t n, void* stream) {
     RZ_REQUIRE(n == 0 || (own && enemy && exactly && move && score), "rz_solve_dev: null pointer");
     if (n == 0) return RZ_OK;
-    size_t blocks = (n + solver::kWarpsPerBlock - 1) / solver::kWarpsPerBlock;
-    const size_t cap = (size_t)num_sms() * 4;
-    if (blocks > cap) blocks = cap;
-    // per-warp transposition tables (kept for the life of the process; entries are position facts and never go stale)
+    const size_t blocks = (size_t)num_sms() * 2;
+    const size_t lanes = blocks * solver::kBlockThreads;
+    // per-lane request contexts and transposition tables (kept for the life of the process; table entries are position
+    // facts and never go stale)
+    static solver::SolveCtx* scratch = nullptr;
     static u64* tt_base = nullptr;
-    static size_t tt_warps = 0;
-    if (tt_warps < cap * solver::kWarpsPerBlock) {
-        if (tt_base) cudaFree(tt_base);
-        tt_base = nullptr; tt_warps = 0;
-        const size_t bytes = cap * solver::kWarpsPerBlock * (size_t)solver::kTtEntries * solver::kTtWordsPerEntry * sizeof(u64);
-        RZ_CUDA_TRY(cudaMalloc((void**)&tt_base, bytes));
-        RZ_CUDA_TRY(cudaMemsetAsync(tt_base, 0, bytes, (cudaStream_t)stream));
-        tt_warps = cap * solver::kWarpsPerBlock;
+    if (!scratch) {
+        const size_t tt_bytes = lanes * (size_t)solver::kTtEntries * solver::kTtWordsPerEntry * sizeof(u64);
+        RZ_CUDA_TRY(cudaMalloc((void**)&tt_base, tt_bytes));
+        RZ_CUDA_TRY(cudaMemsetAsync(tt_base, 0, tt_bytes, (cudaStream_t)stream));
+        RZ_CUDA_TRY(cudaMalloc((void**)&scratch, lanes * sizeof(solver::SolveCtx)));
     }
-    solver::solve_kernel<<<(unsigned)blocks, solver::kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(own, enemy, exactly, move, score, n, tt_base);
+    solver::solve_kernel<<<(unsigned)blocks, solver::kBlockThreads, 0, (cudaStream_t)stream>>>(own, enemy, exactly, move, score, n, scratch, tt_base);
     RZ_LAUNCH_CHECK();
     return RZ_OK;
 }

@@ -224,10 +224,15 @@ def test_evaluate_worker_with_real_networks(tmp_path):
 @pytest.mark.parametrize("kw", [dict(use_solver_turn=52, use_solver_turn_in_simulation=52, simulation_num_per_move=24),
                                 dict(use_solver_turn=56, use_solver_turn_in_simulation=50, simulation_num_per_move=32, parallel_search_num=4),
                                 dict(use_solver_turn=0, use_solver_turn_in_simulation=51, simulation_num_per_move=20)])
-def test_full_games_with_endgame_solver_exact(kw):
+@pytest.mark.parametrize("budget_us", [None, 1])
+def test_full_games_with_endgame_solver_exact(kw, budget_us, monkeypatch):
     """endgame solver hooks on the device (agent/player.py:100-103,150-161,237-251): exact root solves from
     use_solver_turn on (plies not recorded) and WLD-solved nodes inside the search; whole games equal the oracle (which
-    equals the reference, tests/test_oracle.py::test_mcts_with_solver_exact_vs_reference)."""
+    equals the reference, tests/test_oracle.py::test_mcts_with_solver_exact_vs_reference).  Solves are resumable and
+    advance for a bounded time per wave; budget_us = 1 makes every solve span many waves (slots wait, network results of
+    the waiting slots are kept aside) -- the games must not change."""
+    if budget_us is not None:
+        monkeypatch.setenv("RZ_SOLVER_BUDGET_US", str(budget_us))
     pp = params(**kw)
     n_games = 5
     eng = make_engine(pp, games=3, seed=51, max_games=n_games)
