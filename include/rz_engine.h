@@ -271,6 +271,37 @@ int rz_engine_search_root(rz_engine* e, uint64_t own, uint64_t enemy, int player
 int rz_write_play_data(const char* path, const rz_game* games, size_t n_games, const rz_ply* plies,
                        int save_policy_of_tau_1, int change_tau_turn, size_t* n_records);
 
+/* ------------------------------------------------------------------------------------------------
+ * Trainer-side ingest -- replaces the pure-Python per-record loop of
+ * OptimizeWorker.convert_to_training_data (worker/optimize.py:215-231) applied to
+ * read_game_data_from_file (lib/data_helper.py:28-30).
+ *
+ * A "play row" is one recorded ply before the 8-symmetry expansion: 280 bytes instead of ~11 KB of JSON text.
+ * rz_write_play_rows writes the rows of the same games, in the same order, as rz_write_play_data writes records
+ * (file: 32-byte header {"RZROWS\0\1", int32 save_policy_of_tau_1, int32 change_tau_turn, uint64 n_rows, 8 bytes 0}
+ * + n_rows rows).  rz_ingest[_dev] expands rows into the arrays the reference trainer builds from the JSON file:
+ *   planes [8*n_rows][2][8][8] uint8   == np.array(state_list)   (bit_to_array, lib/bitboard.py:136-138)
+ *   policy [8*n_rows][64]      float32 == np.array(policy_list) rounded to the float32 Keras feeds the model
+ *   z      [8*n_rows]          float32 == np.array(z_list)
+ * row r, symmetry t (t = flip*4 + rot, agent/player.py:166-179) -> output record 8*r + t.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rz_play_row {
+    uint64_t own, enemy;  /* position in the mover's frame */
+    int32_t n_visit[64];  /* root visit counts at decision time */
+    int32_t z;            /* game result from the mover's point of view: +1 / 0 / -1 */
+    int32_t pad;
+} rz_play_row;
+
+int rz_write_play_rows(const char* path, const rz_game* games, size_t n_games, const rz_ply* plies,
+                       int save_policy_of_tau_1, int change_tau_turn, size_t* n_rows);
+/* rows == NULL: only report n_rows and the two policy settings stored in the header */
+int rz_read_play_rows(const char* path, rz_play_row* rows, size_t capacity, size_t* n_rows,
+                      int* save_policy_of_tau_1, int* change_tau_turn);
+int rz_ingest_dev(const rz_play_row* rows, size_t n_rows, int save_policy_of_tau_1, int change_tau_turn,
+                  uint8_t* planes, float* policy, float* z, void* stream);   /* device pointers */
+int rz_ingest(const rz_play_row* rows, size_t n_rows, int save_policy_of_tau_1, int change_tau_turn,
+              uint8_t* planes, float* policy, float* z);                       /* host pointers */
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,199 @@
+// rz_ingest.cu -- trainer-side ingest: compact play rows -> training arrays on the device, and the
+// binary row file written next to play_*.json.  Replaces the per-record Python loop of
+// OptimizeWorker.convert_to_training_data (worker/optimize.py:215-231) over json.load (lib/data_helper.py:28-30).
+//
+// HBM-bound byte work: per row the kernel reads 280 B and writes 8 x (128 + 256 + 4) = 3104 B.  One 256-thread CTA
+// expands 4 rows per iteration, 64 threads per row: phase A loads the 64 visit counts (one per thread, 256 B coalesced),
+// reduces sum / first arg-max with shuffles and leaves the stored policy and the 16 transformed boards in shared memory;
+// phase B writes the row's 8 records as 16-byte vector stores (8 per record for the planes, 16 for the policy, through a
+// 512-byte inverse-permutation table), consecutive threads covering consecutive 16-byte pieces of a record.
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include "rz_bitboard.cuh"
+#include "rz_common.cuh"
+
+namespace rz {
+
+constexpr int kIngestThreads = 256;
+constexpr int kRowsPerIter = kIngestThreads / 64;
+
+__device__ __forceinline__ uint32_t bits4_to_bytes(uint32_t b) { return (b * 0x00204081u) & 0x01010101u; }  // bit i -> byte i (b < 16)
+
+__global__ void __launch_bounds__(kIngestThreads) ingest_kernel(const rz_play_row* __restrict__ rows, size_t n_rows, int save_tau1,
+                                                                int change_tau_turn, uint8_t* __restrict__ planes,
+                                                                float* __restrict__ policy, float* __restrict__ z) {
+    __shared__ __align__(16) float pol_s[kRowsPerIter][64];
+    __shared__ u64 brd_s[kRowsPerIter][8][2];
+    __shared__ long long sum_s[kRowsPerIter][2];
+    __shared__ int arg_s[kRowsPerIter][2], argn_s[kRowsPerIter][2];
+    __shared__ uint8_t src_s[8][64];  // src_s[t][a] = the square whose policy entry lands on square a under symmetry t
+    const int sub = threadIdx.x >> 6, sq = threadIdx.x & 63, lane = threadIdx.x & 31, half = (threadIdx.x >> 5) & 1;
+    for (int i = threadIdx.x; i < 512; i += kIngestThreads) {
+        const int t = i >> 6, a = i & 63;
+        // the policy moves with the stones: out[dihedral_square(s, t)] = pol[s]  <=>  out[a] = pol[dihedral_square(a, t^-1)];
+        // rotations invert to the opposite rotation, the four reflections (flip + rotation) are involutions
+        src_s[t][a] = (uint8_t)dihedral_square(a, t < 4 ? (4 - t) & 3 : t);
+    }
+    __syncthreads();
+    for (size_t r0 = (size_t)blockIdx.x * kRowsPerIter; r0 < n_rows; r0 += (size_t)gridDim.x * kRowsPerIter) {
+        const size_t r = r0 + sub;
+        const bool live = r < n_rows;
+        const rz_play_row* row = rows + (live ? r : 0);
+        // ---- phase A ----
+        const int n = live ? row->n_visit[sq] : 0;
+        long long s = n;  // sum and first arg-max of the 64 visit counts (np.sum / np.argmax, agent/player.py:377-385)
+        int bn = n, ba = sq;
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            const int on = __shfl_xor_sync(0xffffffffu, bn, o), oa = __shfl_xor_sync(0xffffffffu, ba, o);
+            if (on > bn || (on == bn && oa < ba)) { bn = on; ba = oa; }
+        }
+        if (lane == 0) { sum_s[sub][half] = s; arg_s[sub][half] = ba; argn_s[sub][half] = bn; }
+        if (sq < 16) brd_s[sub][sq >> 1][sq & 1] = dihedral((sq & 1) ? row->enemy : row->own, sq >> 1);  // 8 symmetries of both boards
+        __syncthreads();
+        {
+            const long long total = sum_s[sub][0] + sum_s[sub][1];
+            const int arg = argn_s[sub][1] > argn_s[sub][0] ? arg_s[sub][1] : arg_s[sub][0];  // first maximum: the lower half wins ties
+            const u64 o0 = brd_s[sub][0][0], e0 = brd_s[sub][0][1];  // identity symmetry = the row's position
+            const int turn = popc64(o0) + popc64(e0) - 4;
+            float p;
+            if (save_tau1 || turn < change_tau_turn) p = (float)((double)n / (double)total);  // float64 division, then the float32 cast
+            else p = sq == arg ? 1.f : 0.f;
+            pol_s[sub][sq] = p;
+        }
+        __syncthreads();
+        // ---- phase B: 8 records x (8 + 16) 16-byte pieces = 192 pieces, 3 per thread ----
+        if (live) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int piece = sq + 64 * j, t = piece / 24, part = piece % 24;
+                const size_t rec = r * 8 + t;
+                if (part < 8) {  // 16 squares of one plane: bit -> byte (bit_to_array, lib/bitboard.py:136-138)
+                    const uint32_t bits = (uint32_t)(brd_s[sub][t][part >> 2] >> (16 * (part & 3))) & 0xFFFFu;
+                    const uint4 v = make_uint4(bits4_to_bytes(bits & 15u), bits4_to_bytes((bits >> 4) & 15u), bits4_to_bytes((bits >> 8) & 15u),
+                                               bits4_to_bytes(bits >> 12));
+                    __stcs(reinterpret_cast<uint4*>(planes + rec * 128 + part * 16), v);
+                } else {
+                    const int a0 = (part - 8) * 4;
+                    const uchar4 src = *reinterpret_cast<const uchar4*>(&src_s[t][a0]);
+                    const float4 v = make_float4(pol_s[sub][src.x], pol_s[sub][src.y], pol_s[sub][src.z], pol_s[sub][src.w]);
+                    __stcs(reinterpret_cast<float4*>(policy + rec * 64 + a0), v);
+                }
+            }
+            if (sq < 2) {
+                const float zf = (float)row->z;
+                __stcs(reinterpret_cast<float4*>(z + r * 8 + sq * 4), make_float4(zf, zf, zf, zf));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static const char kMagic[8] = {'R', 'Z', 'R', 'O', 'W', 'S', 0, 1};
+struct RowFileHeader { char magic[8]; int32_t save_tau1, change_tau_turn; uint64_t n_rows; uint64_t zero; };
+static_assert(sizeof(RowFileHeader) == 32, "row file header");
+static_assert(sizeof(rz_play_row) == 280, "play row");
+
+}  // namespace rz
+
+using namespace rz;
+
+extern "C" {
+
+int rz_ingest_dev(const rz_play_row* rows, size_t n_rows, int save_policy_of_tau_1, int change_tau_turn, uint8_t* planes, float* policy,
+                  float* z, void* stream) {
+    RZ_REQUIRE(n_rows == 0 || (rows && planes && policy && z), "rz_ingest_dev: null pointer");
+    if (n_rows == 0) return RZ_OK;
+    size_t blocks = (n_rows + kRowsPerIter - 1) / kRowsPerIter;
+    const size_t cap = (size_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    ingest_kernel<<<(unsigned)blocks, kIngestThreads, 0, (cudaStream_t)stream>>>(rows, n_rows, save_policy_of_tau_1, change_tau_turn, planes,
+                                                                               policy, z);
+    RZ_LAUNCH_CHECK();
+    return RZ_OK;
+}
+
+int rz_ingest(const rz_play_row* rows, size_t n_rows, int save_policy_of_tau_1, int change_tau_turn, uint8_t* planes, float* policy, float* z) {
+    RZ_REQUIRE(n_rows == 0 || (rows && planes && policy && z), "rz_ingest: null pointer");
+    if (n_rows == 0) return RZ_OK;
+    const size_t nrec = n_rows * 8;
+    const size_t b_rows = ((n_rows * sizeof(rz_play_row) + 255) / 256) * 256, b_pl = nrec * 128, b_po = nrec * 64 * sizeof(float);
+    char* d = nullptr;
+    RZ_CUDA_TRY(cudaMalloc((void**)&d, b_rows + b_pl + b_po + nrec * sizeof(float)));
+    rz_play_row* d_rows = (rz_play_row*)d;
+    uint8_t* d_pl = (uint8_t*)(d + b_rows);
+    float* d_po = (float*)(d + b_rows + b_pl);
+    float* d_z = (float*)(d + b_rows + b_pl + b_po);
+    cudaError_t ce = cudaMemcpyAsync(d_rows, rows, n_rows * sizeof(rz_play_row), cudaMemcpyHostToDevice, 0);
+    int rc = RZ_OK;
+    if (ce == cudaSuccess) rc = rz_ingest_dev(d_rows, n_rows, save_policy_of_tau_1, change_tau_turn, d_pl, d_po, d_z, 0);
+    if (ce == cudaSuccess && rc == RZ_OK) ce = cudaMemcpyAsync(planes, d_pl, b_pl, cudaMemcpyDeviceToHost, 0);
+    if (ce == cudaSuccess && rc == RZ_OK) ce = cudaMemcpyAsync(policy, d_po, b_po, cudaMemcpyDeviceToHost, 0);
+    if (ce == cudaSuccess && rc == RZ_OK) ce = cudaMemcpyAsync(z, d_z, nrec * sizeof(float), cudaMemcpyDeviceToHost, 0);
+    if (ce == cudaSuccess && rc == RZ_OK) ce = cudaStreamSynchronize(0);
+    cudaFree(d);
+    if (rc != RZ_OK) return rc;
+    if (ce != cudaSuccess) { set_error("rz_ingest: %s", cudaGetErrorString(ce)); return RZ_ECUDA; }
+    return RZ_OK;
+}
+
+int rz_write_play_rows(const char* path, const rz_game* games, size_t n_games, const rz_ply* plies, int save_policy_of_tau_1,
+                       int change_tau_turn, size_t* n_rows) {
+    RZ_REQUIRE(path && (n_games == 0 || (games && plies)), "rz_write_play_rows: null pointer");
+    std::string out(sizeof(RowFileHeader), '\0');
+    size_t n = 0;
+    for (size_t gi = 0; gi < n_games; ++gi) {
+        const rz_game& g = games[gi];
+        for (int pid = 1; pid <= 2; ++pid) {  // the order of rz_write_play_data: black's plies, then white's (self_play.py:183)
+            for (int i = 0; i < g.n_plies; ++i) {
+                const rz_ply& pl = plies[g.first_ply + i];
+                if (pl.player != pid || !pl.recorded) continue;
+                rz_play_row row;
+                memset(&row, 0, sizeof(row));
+                row.own = pl.own; row.enemy = pl.enemy;
+                memcpy(row.n_visit, pl.n_visit, sizeof(row.n_visit));
+                row.z = pid == 1 ? g.black_z : -g.black_z;
+                out.append((const char*)&row, sizeof(row));
+                ++n;
+            }
+        }
+    }
+    RowFileHeader hd;
+    memcpy(hd.magic, kMagic, 8);
+    hd.save_tau1 = save_policy_of_tau_1; hd.change_tau_turn = change_tau_turn; hd.n_rows = n; hd.zero = 0;
+    memcpy(&out[0], &hd, sizeof(hd));
+    const std::string tmp = std::string(path) + ".tmp";
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) { set_error("rz_write_play_rows: cannot open %s", tmp.c_str()); return RZ_EIO; }
+    const size_t w = fwrite(out.data(), 1, out.size(), f);
+    const int cl = fclose(f);
+    if (w != out.size() || cl != 0) { set_error("rz_write_play_rows: short write to %s", tmp.c_str()); remove(tmp.c_str()); return RZ_EIO; }
+    if (rename(tmp.c_str(), path) != 0) { set_error("rz_write_play_rows: rename to %s failed", path); remove(tmp.c_str()); return RZ_EIO; }
+    if (n_rows) *n_rows = n;
+    return RZ_OK;
+}
+
+int rz_read_play_rows(const char* path, rz_play_row* rows, size_t capacity, size_t* n_rows, int* save_policy_of_tau_1, int* change_tau_turn) {
+    RZ_REQUIRE(path && n_rows, "rz_read_play_rows: null pointer");
+    FILE* f = fopen(path, "rb");
+    if (!f) { set_error("rz_read_play_rows: cannot open %s", path); return RZ_EIO; }
+    RowFileHeader hd;
+    if (fread(&hd, 1, sizeof(hd), f) != sizeof(hd) || memcmp(hd.magic, kMagic, 8) != 0) {
+        fclose(f);
+        set_error("rz_read_play_rows: %s is not a play-row file", path);
+        return RZ_EINVAL;
+    }
+    *n_rows = (size_t)hd.n_rows;
+    if (save_policy_of_tau_1) *save_policy_of_tau_1 = hd.save_tau1;
+    if (change_tau_turn) *change_tau_turn = hd.change_tau_turn;
+    int rc = RZ_OK;
+    if (rows) {
+        if (capacity < hd.n_rows) { set_error("rz_read_play_rows: capacity %zu < %llu rows", capacity, (unsigned long long)hd.n_rows); rc = RZ_ECAPACITY; }
+        else if (fread(rows, sizeof(rz_play_row), (size_t)hd.n_rows, f) != (size_t)hd.n_rows) { set_error("rz_read_play_rows: %s is truncated", path); rc = RZ_EIO; }
+    }
+    fclose(f);
+    return rc;
+}
+
+}  // extern "C"

@@ -50,6 +50,10 @@ class Game(C.Structure):
                 ("black_net", C.c_uint8), ("pad", C.c_uint8 * 2)]
 
 
+class PlayRow(C.Structure):
+    _fields_ = [("own", C.c_uint64), ("enemy", C.c_uint64), ("n_visit", C.c_int32 * 64), ("z", C.c_int32), ("pad", C.c_int32)]
+
+
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("games_started", "games_finished", "expansions", "simulations", "waves",
                                           "plies", "nn_launches", "mcts_launches", "max_nodes_used", "max_edges_used")] + [
@@ -94,6 +98,10 @@ SIGNATURES = {
     "rz_engine_set_resign_threshold": (C.c_int, [vp, C.c_int, C.c_float]),
     "rz_engine_search_root": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, i32p, f32p]),
     "rz_write_play_data": (C.c_int, [C.c_char_p, C.POINTER(Game), sz, C.POINTER(Ply), C.c_int, C.c_int, C.POINTER(sz)]),
+    "rz_write_play_rows": (C.c_int, [C.c_char_p, C.POINTER(Game), sz, C.POINTER(Ply), C.c_int, C.c_int, C.POINTER(sz)]),
+    "rz_read_play_rows": (C.c_int, [C.c_char_p, vp, sz, C.POINTER(sz), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "rz_ingest_dev": (C.c_int, [vp, sz, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "rz_ingest": (C.c_int, [vp, sz, C.c_int, C.c_int, u8p, f32p, f32p]),
 }
 
 _lib = None

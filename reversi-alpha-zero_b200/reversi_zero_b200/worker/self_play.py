@@ -294,6 +294,9 @@ class SelfPlayWorker:
                 game_id += f"_r{self.rank}"
             path = os.path.join(rc.play_data_dir, rc.play_data_filename_tmpl % game_id)
             write_play_data(path, G, len(self.buffer_games), P, pdc.save_policy_of_tau_1, self.config.play.change_tau_turn)
+            if getattr(getattr(self.config, "b200", None), "write_play_rows", False):  # compact twin for worker/ingest.py
+                from .ingest import rows_path_of, write_play_rows
+                write_play_rows(rows_path_of(path), G, len(self.buffer_games), P, pdc.save_policy_of_tau_1, self.config.play.change_tau_turn)
             logger.info(f"save play data to {path}")
             self.files_written.append(path)
             self.buffer_games = []
@@ -314,10 +317,11 @@ class SelfPlayWorker:
         if len(files) < self.config.play_data.max_file_num:
             return
         for i in range(len(files) - self.config.play_data.max_file_num):
-            try:
-                os.remove(files[i])
-            except OSError:
-                pass
+            for victim in (files[i], os.path.splitext(files[i])[0] + ".rzrows"):  # the JSON file and its compact twin, if any
+                try:
+                    os.remove(victim)
+                except OSError:
+                    pass
 
 
 def _copy(struct):

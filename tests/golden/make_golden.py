@@ -291,8 +291,42 @@ def gen_mcts_solver():
     return out
 
 
+def gen_ingest():
+    """Trainer-side ingest: whole reference games -> the reference's own play_data file
+    (lib/data_helper.py:23-25) -> its own loader + OptimizeWorker.convert_to_training_data (worker/optimize.py:215-231).
+    Stored: the compact rows (one per recorded ply, black's then white's as in worker/self_play.py:183) and the arrays
+    the reference trainer builds."""
+    import tempfile
+    from reversi_zero.lib.data_helper import write_game_data_to_file, read_game_data_from_file
+    from reversi_zero.worker.optimize import OptimizeWorker
+    out = {}
+    for name, tau1, ctt, sims in (("tau1", True, 4, 20), ("tau_rule", False, 4, 16), ("one_hot", False, 0, 10)):
+        cfg = ref_config(sims=sims, k=1, noise_eps=0, change_tau_turn=ctt)
+        cfg.play_data.save_policy_of_tau_1 = tau1
+        plies, recs, z = ref_selfplay_game(cfg, FakeNet())
+        rows = [pl for pid in (1, 2) for pl in plies if pl["pid"] == pid]
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, "play_x.json")
+            write_game_data_to_file(path, recs)
+            states, policies, zs = OptimizeWorker.convert_to_training_data(read_game_data_from_file(path))
+        assert states.shape == (8 * len(rows), 2, 8, 8) and states.dtype == np.uint8
+        out[name + "_settings"] = np.array([int(tau1), ctt], np.int32)
+        out[name + "_own"] = np.array([r["own"] for r in rows], U64)
+        out[name + "_enemy"] = np.array([r["enemy"] for r in rows], U64)
+        out[name + "_n_visit"] = np.array([r["N"] for r in rows], np.int32)
+        out[name + "_row_z"] = np.array([z if r["pid"] == 1 else -z for r in rows], np.int32)
+        out[name + "_states_packed"] = np.packbits(states.reshape(len(states), -1), axis=1, bitorder="little")
+        out[name + "_policy"] = policies.astype(np.float64)
+        out[name + "_z"] = zs.astype(np.int64)
+    return out
+
+
 def main():
     import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "ingest":   # only (re)generate the trainer-ingest fixture
+        np.savez_compressed(os.path.join(HERE, "ingest.npz"), **gen_ingest())
+        print("ingest golden vectors written")
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "solver":   # only (re)generate the solver fixtures
         with open(os.path.join(HERE, "solver.json"), "w") as f:
             json.dump(dict(positions=gen_solver(), mcts=gen_mcts_solver()), f)
@@ -310,6 +344,7 @@ def main():
         json.dump(sym, f)
     with open(os.path.join(HERE, "mcts.json"), "w") as f:
         json.dump(mcts, f)
+    np.savez_compressed(os.path.join(HERE, "ingest.npz"), **gen_ingest())
     print("golden vectors written to", HERE)
 
 

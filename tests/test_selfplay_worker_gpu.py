@@ -35,6 +35,7 @@ def mini_config(tmp_path):
 
 def test_mini_selfplay_files(tmp_path):
     cfg = mini_config(tmp_path)
+    cfg.b200.write_play_rows = True   # compact twin of every play_*.json for the device-side trainer ingest
     w = SelfPlayWorker(cfg)
     n = w.start(max_games=10)
     assert n >= 10
@@ -58,6 +59,21 @@ def test_mini_selfplay_files(tmp_path):
         o0, e0 = data[0][0]
         assert data[1][0] == [ob.rotate90(o0), ob.rotate90(e0)] and data[4][0] == [ob.flip_vertical(o0), ob.flip_vertical(e0)]
     assert n_rec > 0
+    # trainer-side ingest: the row file next to each JSON file expands, on the device, to exactly the arrays
+    # the reference trainer builds from the JSON (worker/optimize.py:215-231); pruning removed the twins of pruned files
+    from reversi_zero_b200.worker import ingest as zi
+    assert sorted(glob.glob(os.path.join(cfg.resource.play_data_dir, "play_*.rzrows"))) == [zi.rows_path_of(f) for f in files]
+    for f in files:
+        rows, tau1, ctt = zi.read_play_rows(zi.rows_path_of(f))
+        states, policy, z = zi.to_training_arrays(rows, tau1, ctt)
+        data = json.load(open(f))
+        assert len(data) == len(states) and (tau1, ctt) == (True, 10)
+        ref_states = np.array([[ob.bit_to_array(st[0], 64).reshape(8, 8), ob.bit_to_array(st[1], 64).reshape(8, 8)] for st, _, _ in data])
+        assert np.array_equal(states, ref_states)
+        assert np.array_equal(policy, np.array([p for _, p, _ in data]).astype(np.float32))
+        assert np.array_equal(z, np.array([zz for _, _, zz in data]).astype(np.float32))
+    ds = zi.load_play_data_dir(cfg.resource.play_data_dir, 0)
+    assert ds[0].shape[0] == n_rec and ds[0].is_cuda and ds[1].shape == (n_rec, 64)
     ggf = glob.glob(os.path.join(cfg.resource.self_play_ggf_data_dir, "*.ggf"))
     assert ggf and all(line.startswith("(;GM[Othello]") for line in open(ggf[0]))
     st = w.engine.stats()
