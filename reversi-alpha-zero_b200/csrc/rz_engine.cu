@@ -929,8 +929,8 @@ int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net, int device, rz_engin
     e->solve_parity[0] = e->solve_parity[1] = 0;
     {
         const char* b = getenv("RZ_SOLVER_BUDGET_US");
-        const long long us = b ? atoll(b) : 4000;
-        e->solver_budget_ns = (us > 0 ? us : 4000) * 1000LL;
+        const long long us = b ? atoll(b) : 2000;
+        e->solver_budget_ns = (us > 0 ? us : 2000) * 1000LL;
     }
     // one transposition table per lane of the solver step's grid (one CTA per SM), one set per slot group
     e->solver_tt_words_per_group = (size_t)num_sms() * solver::kBlockThreads * solver::kTtEntries * solver::kTtWordsPerEntry;

@@ -2,11 +2,11 @@
 // binary row file written next to play_*.json.  Replaces the per-record Python loop of
 // OptimizeWorker.convert_to_training_data (worker/optimize.py:215-231) over json.load (lib/data_helper.py:28-30).
 //
-// HBM-bound byte work: per row the kernel reads 280 B and writes 8 x (128 + 256 + 4) = 3104 B.  One 256-thread CTA
-// expands 4 rows per iteration, 64 threads per row: phase A loads the 64 visit counts (one per thread, 256 B coalesced),
-// reduces sum / first arg-max with shuffles and leaves the stored policy and the 16 transformed boards in shared memory;
-// phase B writes the row's 8 records as 16-byte vector stores (8 per record for the planes, 16 for the policy, through a
-// 512-byte inverse-permutation table), consecutive threads covering consecutive 16-byte pieces of a record.
+// HBM-bound byte work: per row the kernel reads 280 B and writes 8 x (128 + 256 + 4) = 3104 B.  One WARP expands one row
+// (no block barriers in the loop): phase A loads the 64 visit counts (two per lane, 2 x 128 B coalesced), reduces sum /
+// first arg-max with shuffles and leaves the stored policy and the 16 transformed boards in shared memory; phase B writes
+// the row's 8 records as 16-byte vector stores (8 per record for the planes, 16 for the policy, through a 512-byte
+// inverse-permutation table), consecutive lanes covering consecutive 16-byte pieces of a record.
 #include <stdio.h>
 #include <string.h>
 #include <string>
@@ -16,19 +16,28 @@
 namespace rz {
 
 constexpr int kIngestThreads = 256;
-constexpr int kRowsPerIter = kIngestThreads / 64;
+constexpr int kIngestWarps = kIngestThreads / 32;
 
 __device__ __forceinline__ uint32_t bits4_to_bytes(uint32_t b) { return (b * 0x00204081u) & 0x01010101u; }  // bit i -> byte i (b < 16)
 
-__global__ void __launch_bounds__(kIngestThreads) ingest_kernel(const rz_play_row* __restrict__ rows, size_t n_rows, int save_tau1,
+// float32(float64(n) / float64(total)) -- what the trainer feeds the model from the JSON's float64 policy.  For
+// total < 2^24 both integers are exact in float32 and the correctly rounded float32 quotient is the same number: a
+// double-rounding difference needs the exact quotient q within 2^-54 (relative) of a float32 midpoint m = M * 2^E (M odd,
+// 25 bits) without being one; but q - m = (n * 2^-E - M * total) * 2^E / total is a non-zero integer multiple of
+// 2^E / total, i.e. at least 2^-25 / total > 2^-49 relative.
+__device__ __forceinline__ float visit_fraction(int n, long long total) {
+    if (n == 0) return 0.f;
+    if (total < (1LL << 24)) return __fdiv_rn((float)n, (float)total);
+    return (float)((double)n / (double)total);
+}
+
+__global__ void __launch_bounds__(kIngestThreads, 4) ingest_kernel(const rz_play_row* __restrict__ rows, size_t n_rows, int save_tau1,
                                                                 int change_tau_turn, uint8_t* __restrict__ planes,
                                                                 float* __restrict__ policy, float* __restrict__ z) {
-    __shared__ __align__(16) float pol_s[kRowsPerIter][64];
-    __shared__ u64 brd_s[kRowsPerIter][8][2];
-    __shared__ long long sum_s[kRowsPerIter][2];
-    __shared__ int arg_s[kRowsPerIter][2], argn_s[kRowsPerIter][2];
-    __shared__ uint8_t src_s[8][64];  // src_s[t][a] = the square whose policy entry lands on square a under symmetry t
-    const int sub = threadIdx.x >> 6, sq = threadIdx.x & 63, lane = threadIdx.x & 31, half = (threadIdx.x >> 5) & 1;
+    __shared__ __align__(16) float pol_s[kIngestWarps][64];
+    __shared__ u64 brd_s[kIngestWarps][8][2];
+    __shared__ __align__(4) uint8_t src_s[8][64];  // src_s[t][a] = the square whose policy entry lands on square a under symmetry t
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < 512; i += kIngestThreads) {
         const int t = i >> 6, a = i & 63;
         // the policy moves with the stones: out[dihedral_square(s, t)] = pol[s]  <=>  out[a] = pol[dihedral_square(a, t^-1)];
@@ -36,57 +45,55 @@ __global__ void __launch_bounds__(kIngestThreads) ingest_kernel(const rz_play_ro
         src_s[t][a] = (uint8_t)dihedral_square(a, t < 4 ? (4 - t) & 3 : t);
     }
     __syncthreads();
-    for (size_t r0 = (size_t)blockIdx.x * kRowsPerIter; r0 < n_rows; r0 += (size_t)gridDim.x * kRowsPerIter) {
-        const size_t r = r0 + sub;
-        const bool live = r < n_rows;
-        const rz_play_row* row = rows + (live ? r : 0);
-        // ---- phase A ----
-        const int n = live ? row->n_visit[sq] : 0;
-        long long s = n;  // sum and first arg-max of the 64 visit counts (np.sum / np.argmax, agent/player.py:377-385)
-        int bn = n, ba = sq;
+    const size_t n_warps = (size_t)gridDim.x * kIngestWarps;
+    for (size_t r = (size_t)blockIdx.x * kIngestWarps + w; r < n_rows; r += n_warps) {
+        const rz_play_row* row = rows + r;
+        // ---- phase A: sum and first arg-max of the 64 visit counts (np.sum / np.argmax, agent/player.py:377-385) ----
+        const int n0 = row->n_visit[lane], n1 = row->n_visit[lane + 32];
+        long long s = (long long)n0 + (long long)n1;
+        int bn = n1 > n0 ? n1 : n0, ba = n1 > n0 ? lane + 32 : lane;
         for (int o = 16; o > 0; o >>= 1) {
             s += __shfl_xor_sync(0xffffffffu, s, o);
             const int on = __shfl_xor_sync(0xffffffffu, bn, o), oa = __shfl_xor_sync(0xffffffffu, ba, o);
             if (on > bn || (on == bn && oa < ba)) { bn = on; ba = oa; }
         }
-        if (lane == 0) { sum_s[sub][half] = s; arg_s[sub][half] = ba; argn_s[sub][half] = bn; }
-        if (sq < 16) brd_s[sub][sq >> 1][sq & 1] = dihedral((sq & 1) ? row->enemy : row->own, sq >> 1);  // 8 symmetries of both boards
-        __syncthreads();
-        {
-            const long long total = sum_s[sub][0] + sum_s[sub][1];
-            const int arg = argn_s[sub][1] > argn_s[sub][0] ? arg_s[sub][1] : arg_s[sub][0];  // first maximum: the lower half wins ties
-            const u64 o0 = brd_s[sub][0][0], e0 = brd_s[sub][0][1];  // identity symmetry = the row's position
-            const int turn = popc64(o0) + popc64(e0) - 4;
-            float p;
-            if (save_tau1 || turn < change_tau_turn) p = (float)((double)n / (double)total);  // float64 division, then the float32 cast
-            else p = sq == arg ? 1.f : 0.f;
-            pol_s[sub][sq] = p;
+        u64 brd = 0;
+        if (lane < 16) {  // the 8 symmetries of both boards, one per lane
+            brd = dihedral((lane & 1) ? row->enemy : row->own, lane >> 1);
+            brd_s[w][lane >> 1][lane & 1] = brd;
         }
-        __syncthreads();
-        // ---- phase B: 8 records x (8 + 16) 16-byte pieces = 192 pieces, 3 per thread ----
-        if (live) {
+        const u64 own = __shfl_sync(0xffffffffu, brd, 0), enemy = __shfl_sync(0xffffffffu, brd, 1);  // identity symmetry
+        const int turn = popc64(own) + popc64(enemy) - 4;
+        if (save_tau1 || turn < change_tau_turn) {
+            pol_s[w][lane] = visit_fraction(n0, s);
+            pol_s[w][lane + 32] = visit_fraction(n1, s);
+        } else {
+            pol_s[w][lane] = lane == ba ? 1.f : 0.f;
+            pol_s[w][lane + 32] = lane + 32 == ba ? 1.f : 0.f;
+        }
+        __syncwarp();
+        // ---- phase B: 8 records x (8 + 16) 16-byte pieces = 192 pieces, 6 per lane ----
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int piece = sq + 64 * j, t = piece / 24, part = piece % 24;
-                const size_t rec = r * 8 + t;
-                if (part < 8) {  // 16 squares of one plane: bit -> byte (bit_to_array, lib/bitboard.py:136-138)
-                    const uint32_t bits = (uint32_t)(brd_s[sub][t][part >> 2] >> (16 * (part & 3))) & 0xFFFFu;
-                    const uint4 v = make_uint4(bits4_to_bytes(bits & 15u), bits4_to_bytes((bits >> 4) & 15u), bits4_to_bytes((bits >> 8) & 15u),
-                                               bits4_to_bytes(bits >> 12));
-                    __stcs(reinterpret_cast<uint4*>(planes + rec * 128 + part * 16), v);
-                } else {
-                    const int a0 = (part - 8) * 4;
-                    const uchar4 src = *reinterpret_cast<const uchar4*>(&src_s[t][a0]);
-                    const float4 v = make_float4(pol_s[sub][src.x], pol_s[sub][src.y], pol_s[sub][src.z], pol_s[sub][src.w]);
-                    __stcs(reinterpret_cast<float4*>(policy + rec * 64 + a0), v);
-                }
-            }
-            if (sq < 2) {
-                const float zf = (float)row->z;
-                __stcs(reinterpret_cast<float4*>(z + r * 8 + sq * 4), make_float4(zf, zf, zf, zf));
+        for (int j = 0; j < 6; ++j) {
+            const int piece = lane + 32 * j, t = piece / 24, part = piece % 24;
+            const size_t rec = r * 8 + t;
+            if (part < 8) {  // 16 squares of one plane: bit -> byte (bit_to_array, lib/bitboard.py:136-138)
+                const uint32_t bits = (uint32_t)(brd_s[w][t][part >> 2] >> (16 * (part & 3))) & 0xFFFFu;
+                const uint4 v = make_uint4(bits4_to_bytes(bits & 15u), bits4_to_bytes((bits >> 4) & 15u), bits4_to_bytes((bits >> 8) & 15u),
+                                           bits4_to_bytes(bits >> 12));
+                __stcs(reinterpret_cast<uint4*>(planes + rec * 128 + part * 16), v);
+            } else {
+                const int a0 = (part - 8) * 4;
+                const uchar4 src = *reinterpret_cast<const uchar4*>(&src_s[t][a0]);
+                const float4 v = make_float4(pol_s[w][src.x], pol_s[w][src.y], pol_s[w][src.z], pol_s[w][src.w]);
+                __stcs(reinterpret_cast<float4*>(policy + rec * 64 + a0), v);
             }
         }
-        __syncthreads();
+        if (lane < 2) {
+            const float zf = (float)row->z;
+            __stcs(reinterpret_cast<float4*>(z + r * 8 + lane * 4), make_float4(zf, zf, zf, zf));
+        }
+        __syncwarp();
     }
 }
 
@@ -105,7 +112,7 @@ int rz_ingest_dev(const rz_play_row* rows, size_t n_rows, int save_policy_of_tau
                   float* z, void* stream) {
     RZ_REQUIRE(n_rows == 0 || (rows && planes && policy && z), "rz_ingest_dev: null pointer");
     if (n_rows == 0) return RZ_OK;
-    size_t blocks = (n_rows + kRowsPerIter - 1) / kRowsPerIter;
+    size_t blocks = (n_rows + kIngestWarps - 1) / kIngestWarps;
     const size_t cap = (size_t)num_sms() * 8;
     if (blocks > cap) blocks = cap;
     ingest_kernel<<<(unsigned)blocks, kIngestThreads, 0, (cudaStream_t)stream>>>(rows, n_rows, save_policy_of_tau_1, change_tau_turn, planes,

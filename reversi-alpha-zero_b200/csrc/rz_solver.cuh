@@ -115,24 +115,24 @@ RZ_HD bool solve_advance(SolveCtx* c, const TT& tt, long long deadline) {
     const bool exactly = c->exactly != 0;
     const bool cached = !exactly && tt.base != nullptr;
     int d = c->depth;
+    Frame F;  // the frame being worked on lives in registers; c->f[0..d-1] hold its ancestors, c->f[d] is written on suspend
     if (d < 0) {  // first visit: set up the root frame
         const u64 legal = find_correct_moves(c->own, c->enemy);
         if (!legal || 64 - popc64(c->own | c->enemy) > kSolverMaxEmpties) { c->move = -1; c->score = 0; publish_fence(); c->done = 1; return true; }
-        Frame& R = c->f[0];
-        R.own = c->own; R.enemy = c->enemy; R.moves = legal; R.best = -100; R.alpha = -64; R.beta = 64; R.sign = 1; R.cur = -1;
+        F.own = c->own; F.enemy = c->enemy; F.moves = legal; F.best = -100; F.alpha = -64; F.beta = 64; F.sign = 1; F.cur = -1;
         d = 0;
+    } else {
+        F = c->f[d];
     }
     int it = 0;
     while (true) {
-        if (deadline && (++it & 15) == 0 && global_ns() > deadline) { c->depth = (int16_t)d; return false; }
-        Frame& F = c->f[d];
+        if (deadline && (++it & 15) == 0 && global_ns() > deadline) { c->f[d] = F; c->depth = (int16_t)d; return false; }
         if (F.moves == 0 || (!exactly && F.best > 0) || (exactly && F.best >= F.beta)) {
             if (cached && d > 0 && 64 - popc64(F.own | F.enemy) >= kTtMinEmpties) tt.store(F.own, F.enemy, F.best);
             if (d == 0) { c->score = F.best; publish_fence(); c->done = 1; c->depth = 0; return true; }
             const int v = F.best * F.sign;
-            --d;
-            Frame& P = c->f[d];
-            if (P.best < v) { P.best = (int8_t)v; if (d == 0) c->move = P.cur; }
+            F = c->f[--d];
+            if (F.best < v) { F.best = (int8_t)v; if (d == 0) c->move = F.cur; }
             continue;
         }
         // root: ascending order (the reference's tie-break); inner exact nodes: fastest first; WLD: ascending everywhere
@@ -158,15 +158,16 @@ RZ_HD bool solve_advance(SolveCtx* c, const TT& tt, long long deadline) {
             }
         }
         if (d + 1 >= kMaxDepth) { c->move = -1; c->score = 0; publish_fence(); c->done = 1; return true; }  // cannot happen within kSolverMaxEmpties
-        Frame& C = c->f[++d];
+        c->f[d++] = F;  // descend: park this frame, the child becomes the working frame
+        const int8_t p_beta = F.beta;
         if (m) {  // opponent to move
-            C.own = en2; C.enemy = own2; C.moves = m; C.sign = -1;
-            C.alpha = (int8_t)(-F.beta); C.beta = (int8_t)(-lo);
+            F.own = en2; F.enemy = own2; F.moves = m; F.sign = -1;
+            F.alpha = (int8_t)(-p_beta); F.beta = (int8_t)(-lo);
         } else {  // pass: same side again, no sign flip
-            C.own = own2; C.enemy = en2; C.moves = m_self; C.sign = 1;
-            C.alpha = (int8_t)lo; C.beta = F.beta;
+            F.own = own2; F.enemy = en2; F.moves = m_self; F.sign = 1;
+            F.alpha = (int8_t)lo; F.beta = p_beta;
         }
-        C.best = -100; C.cur = -1;
+        F.best = -100; F.cur = -1;
     }
 }
 
