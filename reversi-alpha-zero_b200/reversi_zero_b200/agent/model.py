@@ -106,3 +106,50 @@ def blob_to_weights(mc, blob):
 def blob_digest(blob):
     """sha256 of the blob; plays the role of ReversiModel.fetch_digest (agent/model.py:74-80)."""
     return hashlib.sha256(np.ascontiguousarray(blob, dtype=np.float32).tobytes()).hexdigest()
+
+
+def weights_from_keras_layers(mc, layers):
+    """Weight hand-off from the reference's Keras model without relying on ``model.get_weights()``
+    order (Keras sorts the layers of the two heads by graph depth): ``layers`` is an iterable of
+    ``(layer_name, class_name, [arrays])`` -- e.g. ``[(l.name, l.__class__.__name__, l.get_weights()) for l in
+    model.layers]`` -- in any order.  Layers are matched by CREATION order, which Keras encodes in the numeric suffix of
+    its automatic names (``conv2d_7``, ``batch_normalization_7``, ``dense_1``; the counter may start anywhere when
+    several models were built in the process), following ``ReversiModel.build`` (agent/model.py:28-72): conv0, the
+    residual blocks' convolutions, the policy-head 1x1 convolution, the value-head 1x1 convolution; every convolution is
+    followed by its BatchNormalization; ``policy_out`` / ``value_out`` are named, the remaining Dense layer is the
+    value head's hidden layer.  Returns the ``{name: ndarray}`` dict ``weights_to_blob`` packs."""
+    def suffix(name):
+        tail = name.rsplit("_", 1)[-1]
+        return int(tail) if tail.isdigit() else 0
+
+    convs, bns, dense, named = [], [], [], {}
+    for name, cls, arrays in layers:
+        arrays = [np.asarray(a, dtype=np.float32) for a in arrays]
+        if name in ("policy_out", "value_out"):
+            named[name] = arrays
+        elif cls == "Conv2D":
+            convs.append((suffix(name), arrays))
+        elif cls == "BatchNormalization":
+            bns.append((suffix(name), arrays))
+        elif cls == "Dense":
+            dense.append((suffix(name), arrays))
+    convs.sort(key=lambda t: t[0])
+    bns.sort(key=lambda t: t[0])
+    n_conv = 1 + 2 * mc.res_layer_num + 2
+    if len(convs) != n_conv or len(bns) != n_conv or len(dense) != 1 or set(named) != {"policy_out", "value_out"}:
+        raise ValueError(f"expected {n_conv} Conv2D + {n_conv} BatchNormalization + 1 hidden Dense + policy_out + value_out layers, got "
+                         f"{len(convs)} / {len(bns)} / {len(dense)} / {sorted(named)}")
+    prefixes = ["conv0"] + [f"res{i}.conv{j}" for i in range(mc.res_layer_num) for j in (1, 2)] + ["policy_conv", "value_conv"]
+    w = {}
+    for prefix, (_, conv), (_, bn) in zip(prefixes, convs, bns):
+        if len(conv) != 2 or len(bn) != 4:
+            raise ValueError(f"{prefix}: expected [kernel, bias] and [gamma, beta, moving_mean, moving_variance]")
+        w[f"{prefix}.kernel"], w[f"{prefix}.bias"] = conv
+        w[f"{prefix}.bn_gamma"], w[f"{prefix}.bn_beta"], w[f"{prefix}.bn_mean"], w[f"{prefix}.bn_var"] = bn
+    w["policy_fc.kernel"], w["policy_fc.bias"] = named["policy_out"]
+    w["value_fc1.kernel"], w["value_fc1.bias"] = dense[0][1]
+    w["value_fc2.kernel"], w["value_fc2.bias"] = named["value_out"]
+    for name, shape in tensor_specs(mc):
+        if w[name].shape != tuple(shape):
+            raise ValueError(f"{name}: expected shape {shape}, got {w[name].shape}")
+    return w

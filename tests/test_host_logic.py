@@ -5,6 +5,7 @@
 import os
 import types
 
+import numpy as np
 import pytest
 
 from reversi_zero_b200 import _cabi
@@ -89,3 +90,30 @@ def test_config_overlay_like_reference_yaml():
 def test_rank_game_ids_partition():
     ids = [set(rank_game_ids(r, 4, 100, slots=5, games_per_slot=3)) for r in range(4)]
     assert all(len(s) == 15 for s in ids) and set().union(*ids) == set(range(100, 160))
+
+
+def test_keras_layer_matching_for_weight_handoff():
+    """layers of the reference's Keras model (agent/model.py:28-72) -> blob tensors, matched by creation
+    order (numeric name suffix), independent of the order ``model.layers`` lists the two heads in and of the counter
+    offset a second model in the same process gets."""
+    from reversi_zero_b200.agent import model as M
+    mc = M.ModelConfig(cnn_filter_num=8, res_layer_num=2, value_fc_size=4)
+    w = M.build_random_weights(mc, seed=3, perturb_bn=True)
+    prefixes = ["conv0"] + [f"res{i}.conv{j}" for i in range(2) for j in (1, 2)] + ["policy_conv", "value_conv"]
+    off = 37                                       # e.g. the second model built in the trainer process
+    layers = [("input_2", "InputLayer", [])]
+    for i, p in enumerate(prefixes):
+        layers.append((f"conv2d_{off + i}", "Conv2D", [w[f"{p}.kernel"], w[f"{p}.bias"]]))
+        layers.append((f"batch_normalization_{off + i}", "BatchNormalization", [w[f"{p}.bn_gamma"], w[f"{p}.bn_beta"], w[f"{p}.bn_mean"], w[f"{p}.bn_var"]]))
+        layers.append((f"activation_{off + i}", "Activation", []))
+    layers += [("dense_9", "Dense", [w["value_fc1.kernel"], w["value_fc1.bias"]]), ("policy_out", "Dense", [w["policy_fc.kernel"], w["policy_fc.bias"]]),
+               ("value_out", "Dense", [w["value_fc2.kernel"], w["value_fc2.bias"]]), ("flatten_3", "Flatten", []), ("add_5", "Add", [])]
+    rng = np.random.default_rng(0)
+    for _ in range(3):
+        order = rng.permutation(len(layers))
+        got = M.weights_from_keras_layers(mc, [layers[i] for i in order])
+        assert np.array_equal(M.weights_to_blob(mc, got), M.weights_to_blob(mc, w))
+    with pytest.raises(ValueError):
+        M.weights_from_keras_layers(mc, layers[:-6])          # a head is missing
+    with pytest.raises(ValueError):
+        M.weights_from_keras_layers(M.ModelConfig(cnn_filter_num=16, res_layer_num=2, value_fc_size=4), layers)   # wrong shapes
