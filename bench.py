@@ -133,7 +133,8 @@ def workload_config(args, **extra):
                       "thinking_loop=1 solver=%s resign=off" % (args.games, args.sims, "on(50/50)" if PLAY_KW.get("use_solver_turn") else "off"),
              games_per_gpu=args.games, simulation_num_per_move=PLAY_KW["simulation_num_per_move"],
              l2="leaf batch + per-game trees (>20 GB) exceed L2; weights (23.7 MB fp16) are L2-resident by design",
-             step="one wave = MCTS tick kernel + tcgen05 tower launch over the leaf batch", parallelism=f"dp{args.gpus} (games sharded by rank)")
+             step="one wave = MCTS tick kernel + tcgen05 tower launch over the leaf batch",
+             arithmetic="network: f16 operands, f32 accumulate + f32 residual stream; MCTS: f32 W, f64 PUCT as numpy promotes; rules: u64", parallelism=f"dp{args.gpus} (games sharded by rank)")
     c.update(extra)
     return c
 
@@ -349,7 +350,7 @@ def main():
                   expansions_per_sec=r["expansions_per_s"], mean_nn_batch=r["mean_batch"])
 
     line = dict(metric="self_play_games_per_sec", value=value, unit="games/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=run_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16 operands / f32 accumulate",
+                ms_per_step=run_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16",
                 data="synthetic (random-init ch5 weights, self-generated games)",
                 config=workload_config(args, games_finished_in_window=games, games_per_sec_finished_in_window=games / secs,
                                        plies_decided=plies, expansions_per_game=epg, expansions_per_game_source=epg_src,
