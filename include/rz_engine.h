@@ -170,7 +170,10 @@ typedef struct rz_engine_cfg {
     int32_t use_solver_turn;        /* PlayConfig.use_solver_turn (config.py:154): from this turn on the move is the exact
                                        endgame solution (agent/player.py:100-103,150-161) and the ply is not training data;
                                        0 = off.  Positions the device solver refuses (> 12 empties) are searched instead. */
-    int32_t use_solver_turn_in_simulation; /* :155, agent/player.py:237-251: WLD-solved nodes inside the search; 0 = off */
+    int32_t use_solver_turn_in_simulation; /* :155, agent/player.py:237-251: WLD-solved nodes inside the search; 0 = off.
+                                       Solves are resumable: each wave advances the unfinished ones for at most
+                                       RZ_SOLVER_BUDGET_US microseconds (environment, read by rz_engine_create; default
+                                       2000) and a game waits until its solves are done -- results do not depend on it. */
     int32_t reset_mtcs_info_per_game; /* PlayConfig.reset_mtcs_info_per_game (config.py:131; worker/self_play.py:111-134): a
                                        slot keeps its statistics for this many consecutive games (0 / 1: every game starts
                                        empty, ch5.yml; mini.yml uses 3).  Arenas grow by the same factor. */

@@ -744,6 +744,7 @@ static int collect_timing(rz_engine* e) {  // call after the stream has been syn
 }
 
 static int dev_alloc(rz_engine* e, void** ptr, size_t bytes, bool zero) {
+    if (e->n_arena >= (int)(sizeof(e->arena) / sizeof(e->arena[0]))) { set_error("rz_engine: allocation table full"); return RZ_ESTATE; }
     cudaError_t ce = cudaMalloc(ptr, bytes);
     if (ce != cudaSuccess) {
         set_error("rz_engine: cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(ce));
