@@ -12,6 +12,15 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "reversi-alpha-zero_b200"))
 
 
+def d_out_check(lib, D, d_own, d_enemy, n):
+    import numpy as np
+    out = D.empty(n, np.uint64)
+    lib.rz_find_correct_moves_dev(D.ptr(d_own), D.ptr(d_enemy), D.ptr(out), n, D.stream_ptr())
+    import torch
+    torch.cuda.synchronize()
+    return out
+
+
 def run(n=10_000_000, iters=100, warmup=5):
     import torch
     from reversi_zero_b200 import _cabi, device as D
@@ -52,6 +61,16 @@ def run(n=10_000_000, iters=100, warmup=5):
     from oracle import bitboard as ob
     t = time.time(); ob.find_correct_moves_batch(own[:2_000_000], enemy[:2_000_000]); dt = time.time() - t
     res["cpu_oracle_find_correct_moves_mpos_per_s_1core"] = 2.0 / dt
+    # the reference's own compiled Cython (oracle/_ref, built from lib/alt/bitboard_cython.pyx) on one core
+    from oracle import ref_native
+    if ref_native.available():
+        bb, _ = ref_native.load()
+        m = 500_000
+        t = time.time()
+        ref = np.fromiter((bb.find_correct_moves(int(o), int(e)) for o, e in zip(own[:m], enemy[:m])), dtype=np.uint64, count=m)
+        dt = time.time() - t
+        res["cpu_reference_cython_find_correct_moves_mpos_per_s_1core"] = m / dt / 1e6
+        res["cpu_reference_matches_first_500k"] = bool(np.array_equal(ref, D.to_numpy_u64(d_out_check(lib, D, d_own, d_enemy, n))[:m]))
     res["n"] = n
     res["hbm_peak_gbs"] = hbm
     return res
