@@ -125,7 +125,7 @@ def run_reference(args):
                 data="synthetic", config=workload_config(args, cores=cores), node_expansions_per_sec=eps,
                 cpu_baseline=dict(value=gps, unit="games/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=gps, unit="games/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
 
 
 def workload_config(args, **extra):
@@ -220,7 +220,7 @@ def main():
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", "full_games_solver.json" if args.solver else "full_games.json"), "w") as f:
             json.dump(out, f)
-        print(json.dumps(out), flush=True)
+        _emit(json.dumps(out))
         return
 
     # ---- device-resident measurement: `value` -------------------------------------------------------------
@@ -362,10 +362,20 @@ def main():
                          play_data_bytes_written=file_bytes, games_harvested=n_e2e_all, expansions=e2e_exps, seconds=e2e_secs,
                          what="host weight blob -> device + pack, engine create, K waves, harvest, play_*.json written"),
                 gpu_launches=int(launches))
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+def _emit(text):
+    """The result line goes to the REAL stdout; everything else this process (or a library such as NCCL, which prints its
+    version banner to stdout) writes to file descriptor 1 during the run is diverted to stderr, so stdout carries
+    exactly one JSON line."""
+    os.write(_REAL_STDOUT, (text + "\n").encode())
+
+
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     main()
