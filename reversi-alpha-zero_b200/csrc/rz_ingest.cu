@@ -5,8 +5,9 @@
 // HBM-bound byte work: per row the kernel reads 280 B and writes 8 x (128 + 256 + 4) = 3104 B.  One WARP expands one row
 // (no block barriers in the loop): phase A loads the 64 visit counts (two per lane, 2 x 128 B coalesced), reduces sum /
 // first arg-max with shuffles and leaves the stored policy and the 16 transformed boards in shared memory; phase B writes
-// the row's 8 records as 16-byte vector stores (8 per record for the planes, 16 for the policy, through a 512-byte
-// inverse-permutation table), consecutive lanes covering consecutive 16-byte pieces of a record.
+// the row's 8 records as 16-byte vector stores (64 for the planes, 128 for the policy through a 512-byte inverse-
+// permutation table); the 8 records of a row are contiguous in every output array, so each warp store instruction covers
+// 512 consecutive bytes and the loops are free of divergence.
 #include <stdio.h>
 #include <string.h>
 #include <string>
@@ -72,22 +73,22 @@ __global__ void __launch_bounds__(kIngestThreads, 4) ingest_kernel(const rz_play
             pol_s[w][lane + 32] = lane + 32 == ba ? 1.f : 0.f;
         }
         __syncwarp();
-        // ---- phase B: 8 records x (8 + 16) 16-byte pieces = 192 pieces, 6 per lane ----
+        // ---- phase B: the row's 8 records are contiguous in each output array: planes 8 x 128 B = 64 sixteen-byte pieces
+        //      (2 per lane), policy 8 x 256 B = 128 pieces (4 per lane); a warp store covers 512 consecutive bytes ----
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            const int piece = lane + 32 * j, t = piece / 24, part = piece % 24;
-            const size_t rec = r * 8 + t;
-            if (part < 8) {  // 16 squares of one plane: bit -> byte (bit_to_array, lib/bitboard.py:136-138)
-                const uint32_t bits = (uint32_t)(brd_s[w][t][part >> 2] >> (16 * (part & 3))) & 0xFFFFu;
-                const uint4 v = make_uint4(bits4_to_bytes(bits & 15u), bits4_to_bytes((bits >> 4) & 15u), bits4_to_bytes((bits >> 8) & 15u),
-                                           bits4_to_bytes(bits >> 12));
-                __stcs(reinterpret_cast<uint4*>(planes + rec * 128 + part * 16), v);
-            } else {
-                const int a0 = (part - 8) * 4;
-                const uchar4 src = *reinterpret_cast<const uchar4*>(&src_s[t][a0]);
-                const float4 v = make_float4(pol_s[w][src.x], pol_s[w][src.y], pol_s[w][src.z], pol_s[w][src.w]);
-                __stcs(reinterpret_cast<float4*>(policy + rec * 64 + a0), v);
-            }
+        for (int j = 0; j < 2; ++j) {  // 16 squares of one plane: bit -> byte (bit_to_array, lib/bitboard.py:136-138)
+            const int piece = lane + 32 * j, t = piece >> 3, part = piece & 7;
+            const uint32_t bits = (uint32_t)(brd_s[w][t][part >> 2] >> (16 * (part & 3))) & 0xFFFFu;
+            const uint4 v = make_uint4(bits4_to_bytes(bits & 15u), bits4_to_bytes((bits >> 4) & 15u), bits4_to_bytes((bits >> 8) & 15u),
+                                       bits4_to_bytes(bits >> 12));
+            __stcs(reinterpret_cast<uint4*>(planes + r * 1024) + piece, v);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int piece = lane + 32 * j, t = piece >> 4, a0 = (piece & 15) * 4;
+            const uchar4 src = *reinterpret_cast<const uchar4*>(&src_s[t][a0]);
+            const float4 v = make_float4(pol_s[w][src.x], pol_s[w][src.y], pol_s[w][src.z], pol_s[w][src.w]);
+            __stcs(reinterpret_cast<float4*>(policy + r * 512) + piece, v);
         }
         if (lane < 2) {
             const float zf = (float)row->z;
