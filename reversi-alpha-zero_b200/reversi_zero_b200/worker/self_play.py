@@ -51,14 +51,19 @@ def _b200(config):
     return getattr(config, "b200", None) or B200Config()
 
 
+NEXT_GENERATION_BLOB = "model_weight.rzblob.npy"  # next to model_weight.h5 in next_generation/model_*/ (tools/export_keras_weights.py)
+
+
 def load_or_build_weights(config, net):
-    """agent/api.py:102-115 load_model: best weights if present, else build() + save_as_best (``--new``).
-    The engine-side hand-off file is a float32 .npy blob (h5 import from the Keras trainer: SURVEY 8(f).1)."""
-    path = blob_path_of(config)
-    if not getattr(config.opts, "new", False) and os.path.exists(path):
+    """agent/api.py:102-115 load_model: with ``play.use_newest_next_generation_model`` (the default, config.py:166) the
+    newest next-generation weights, else -- or if there are none -- the best weights; nothing there (or ``--new``):
+    build() + save_as_best.  The engine-side hand-off files are float32 .npy blobs."""
+    path = None if getattr(config.opts, "new", False) else weight_source_path(config)
+    if path is not None:
         blob = np.load(path)
         logger.debug(f"loading weights from {path}")
     else:
+        path = blob_path_of(config)
         blob = M.weights_to_blob(config.model, M.build_random_weights(config.model, _b200(config).weight_seed))
         os.makedirs(os.path.dirname(path), exist_ok=True)
         np.save(path, blob)
@@ -70,6 +75,28 @@ def load_or_build_weights(config, net):
 def blob_path_of(config):
     rc = config.resource
     return getattr(rc, "model_best_blob_path", os.path.join(rc.model_dir, "model_best_weight.rzblob.npy"))
+
+
+def newest_next_generation_blob(config):
+    """lib/model_helpler.py:50-63 + lib/data_helper.py:17-20: the weight blob in the last (sorted) next_generation/model_* directory"""
+    from glob import glob
+    rc = config.resource
+    base = getattr(rc, "next_generation_model_dir", os.path.join(rc.model_dir, "next_generation"))
+    tmpl = getattr(rc, "next_generation_model_dirname_tmpl", "model_%s")
+    for d in reversed(sorted(glob(os.path.join(base, tmpl % "*")))):
+        path = os.path.join(d, NEXT_GENERATION_BLOB)
+        return path if os.path.exists(path) else None   # only the newest directory counts, like the reference
+    return None
+
+
+def weight_source_path(config):
+    """The file self-play takes its weights from right now (agent/api.py:107-110,120-123), or None."""
+    best = blob_path_of(config)
+    best = best if os.path.exists(best) else None
+    newest = newest_next_generation_blob(config)
+    if getattr(config.play, "use_newest_next_generation_model", True):
+        return newest or best
+    return best or newest
 
 
 class SelfPlayWorker:
@@ -138,7 +165,11 @@ class SelfPlayWorker:
         if not force_check and time.time() - self.last_model_check_time < self.MODEL_CHECK_INTERVAL_SEC:
             return False
         self.last_model_check_time = time.time()
-        path = blob_path_of(self.config)
+        # agent/api.py:117-125: the newest next-generation model if configured (and present), else the best model (the
+        # reference checks ONLY the newest model when configured; also looking at the best file when there is no
+        # next-generation model is a harmless superset: after a promotion both hold the same weights)
+        newest = newest_next_generation_blob(self.config) if getattr(self.config.play, "use_newest_next_generation_model", True) else None
+        path = newest or blob_path_of(self.config)
         blob = None
         changed = False
         if self.rank == 0 and os.path.exists(path):

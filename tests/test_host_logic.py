@@ -117,3 +117,30 @@ def test_keras_layer_matching_for_weight_handoff():
         M.weights_from_keras_layers(mc, layers[:-6])          # a head is missing
     with pytest.raises(ValueError):
         M.weights_from_keras_layers(M.ModelConfig(cnn_filter_num=16, res_layer_num=2, value_fc_size=4), layers)   # wrong shapes
+
+
+def test_weight_source_selection(tmp_path):
+    """agent/api.py:102-125 + lib/model_helpler.py: which weights self-play starts from / reloads -- newest next-generation
+    model first when play.use_newest_next_generation_model (the default), best model otherwise."""
+    from reversi_zero_b200.worker import self_play as sp
+    cfg = Config(project_dir=str(tmp_path), data_dir=str(tmp_path / "data"))
+    cfg.resource.create_directories()
+    assert sp.weight_source_path(cfg) is None and sp.newest_next_generation_blob(cfg) is None
+    best = sp.blob_path_of(cfg)
+    np.save(best, np.zeros(3, np.float32))
+    assert sp.weight_source_path(cfg) == best
+    dirs = []
+    for stamp in ("20260101-000000.000000", "20260301-000000.000000"):
+        d = os.path.join(cfg.resource.next_generation_model_dir, cfg.resource.next_generation_model_dirname_tmpl % stamp)
+        os.makedirs(d)
+        dirs.append(d)
+    np.save(os.path.join(dirs[0], sp.NEXT_GENERATION_BLOB), np.ones(3, np.float32))
+    assert sp.newest_next_generation_blob(cfg) is None            # only the newest directory counts, and it has no blob yet
+    assert sp.weight_source_path(cfg) == best
+    newest = os.path.join(dirs[1], sp.NEXT_GENERATION_BLOB)
+    np.save(newest, np.ones(3, np.float32))
+    assert cfg.play.use_newest_next_generation_model is True and sp.weight_source_path(cfg) == newest
+    cfg.play.use_newest_next_generation_model = False
+    assert sp.weight_source_path(cfg) == best
+    os.remove(best)
+    assert sp.weight_source_path(cfg) == newest                   # load_best_model_weight(...) or reload_newest_...(...)
