@@ -119,7 +119,7 @@ struct Slot {
     uint8_t root_pid, black_net, cur_net;  // black_net / cur_net: evaluation matches (two networks)
     uint8_t root_req;         // 1: an exact root solve has to be put into this wave's solver batch
     uint8_t pad[4];
-    uint32_t root_solve_index, n_solves, n_searched_plies, pad2;
+    uint32_t n_solves, n_searched_plies;
 };
 
 struct Status {

@@ -1,4 +1,5 @@
-"""Latency of the device endgame solver per request: one batch = one request per resident warp."""
+"""Latency of the device endgame solver (rz_solve_dev): one batch = one request per lane of its grid (2 CTAs x 128 lanes
+per SM), every lane running its own resumable stack machine to completion."""
 import json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -23,7 +24,7 @@ def main():
     import torch
     from reversi_zero_b200 import _cabi, device as D
     lib = _cabi.lib()
-    n = 592 * 4  # resident warps of the kernel's grid
+    n = 148 * 2 * 128  # lanes of the kernel's grid
     for empties in (8, 10):
         own, enemy = positions(empties, 400, empties)
         own = np.resize(own, n); enemy = np.resize(enemy, n)
