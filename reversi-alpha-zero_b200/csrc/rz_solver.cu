@@ -41,16 +41,25 @@ int rz_solve_dev(const uint64_t* own, const uint64_t* enemy, const uint8_t* exac
     if (n == 0) return RZ_OK;
     const size_t blocks = (size_t)num_sms() * 2;
     const size_t lanes = blocks * solver::kBlockThreads;
-    // per-lane request contexts and transposition tables (kept for the life of the process; table entries are position
-    // facts and never go stale)
-    static solver::SolveCtx* scratch = nullptr;
-    static u64* tt_base = nullptr;
-    if (!scratch) {
+    // per-lane request contexts and transposition tables, one set per device (kept for the life of the process; table
+    // entries are position facts and never go stale).  Concurrent calls on one device must use one stream at a time.
+    constexpr int kMaxDevices = 64;
+    static solver::SolveCtx* scratch_of[kMaxDevices] = {};
+    static u64* tt_of[kMaxDevices] = {};
+    int dev = 0;
+    RZ_CUDA_TRY(cudaGetDevice(&dev));
+    RZ_REQUIRE(dev >= 0 && dev < kMaxDevices, "rz_solve_dev: device index out of range");
+    if (!scratch_of[dev]) {
         const size_t tt_bytes = lanes * (size_t)solver::kTtEntries * solver::kTtWordsPerEntry * sizeof(u64);
-        RZ_CUDA_TRY(cudaMalloc((void**)&tt_base, tt_bytes));
-        RZ_CUDA_TRY(cudaMemsetAsync(tt_base, 0, tt_bytes, (cudaStream_t)stream));
-        RZ_CUDA_TRY(cudaMalloc((void**)&scratch, lanes * sizeof(solver::SolveCtx)));
+        u64* t = nullptr;
+        RZ_CUDA_TRY(cudaMalloc((void**)&t, tt_bytes));
+        RZ_CUDA_TRY(cudaMemsetAsync(t, 0, tt_bytes, (cudaStream_t)stream));
+        solver::SolveCtx* c = nullptr;
+        RZ_CUDA_TRY(cudaMalloc((void**)&c, lanes * sizeof(solver::SolveCtx)));
+        tt_of[dev] = t; scratch_of[dev] = c;
     }
+    solver::SolveCtx* scratch = scratch_of[dev];
+    u64* tt_base = tt_of[dev];
     solver::solve_kernel<<<(unsigned)blocks, solver::kBlockThreads, 0, (cudaStream_t)stream>>>(own, enemy, exactly, move, score, n, scratch, tt_base);
     RZ_LAUNCH_CHECK();
     return RZ_OK;
