@@ -279,7 +279,7 @@ int rz_write_play_data(const char* path, const rz_game* games, size_t n_games, c
  * OptimizeWorker.convert_to_training_data (worker/optimize.py:215-231) applied to
  * read_game_data_from_file (lib/data_helper.py:28-30).
  *
- * A "play row" is one recorded ply before the 8-symmetry expansion: 280 bytes instead of ~11 KB of JSON text.
+ * A "play row" is one recorded ply before the 8-symmetry expansion: 280 bytes instead of ~5 KB of JSON text.
  * rz_write_play_rows writes the rows of the same games, in the same order, as rz_write_play_data writes records
  * (file: 32-byte header {"RZROWS\0\1", int32 save_policy_of_tau_1, int32 change_tau_turn, uint64 n_rows, 8 bytes 0}
  * + n_rows rows).  rz_ingest[_dev] expands rows into the arrays the reference trainer builds from the JSON file:

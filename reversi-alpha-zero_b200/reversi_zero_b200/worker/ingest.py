@@ -1,6 +1,6 @@
 """Trainer-side ingest: what ``OptimizeWorker.load_play_data`` / ``convert_to_training_data``
 (worker/optimize.py:165-231) do with ``play_*.json`` -- here from the compact row files the self-play worker can
-write next to them (``play_*.rzrows``, 280 bytes per recorded ply instead of ~11 KB of JSON per ply), expanded to
+write next to them (``play_*.rzrows``, 280 bytes per recorded ply instead of ~5 KB of JSON per ply), expanded to
 training arrays on the device by ``rz_ingest`` (csrc/rz_ingest.cu).  No CPU fallback.
 
     rows, tau1, ctt = read_play_rows("data/play_data/play_20260922-101500.123456.rzrows")
