@@ -223,7 +223,13 @@ def test_evaluate_worker_with_real_networks(tmp_path):
 
 @pytest.mark.parametrize("kw", [dict(use_solver_turn=52, use_solver_turn_in_simulation=52, simulation_num_per_move=24),
                                 dict(use_solver_turn=56, use_solver_turn_in_simulation=50, simulation_num_per_move=32, parallel_search_num=4),
-                                dict(use_solver_turn=0, use_solver_turn_in_simulation=51, simulation_num_per_move=20)])
+                                dict(use_solver_turn=0, use_solver_turn_in_simulation=51, simulation_num_per_move=20),
+                                # everything at once: solver at the root and inside the search, rethinking loops, separate tables
+                                # per player, resignation (enabled for half of the games), late tau switch
+                                dict(use_solver_turn=54, use_solver_turn_in_simulation=52, simulation_num_per_move=20, parallel_search_num=4,
+                                     thinking_loop=2, required_visit_to_decide_action=30, start_rethinking_turn=2,
+                                     share_mtcs_info_in_self_play=False, resign_threshold=-0.5, allowed_resign_turn=10,
+                                     disable_resignation_rate=0.5, change_tau_turn=8)])
 @pytest.mark.parametrize("budget_us", [None, 1])
 def test_full_games_with_endgame_solver_exact(kw, budget_us, monkeypatch):
     """endgame solver hooks on the device (agent/player.py:100-103,150-161,237-251): exact root solves from
@@ -245,8 +251,10 @@ def test_full_games_with_endgame_solver_exact(kw, budget_us, monkeypatch):
         replay_check(g)
         o = mcts.SelfPlayGame(pp, onn.FakeNetAPI(), seed=51, game_id=g["game_id"]).play()
         theirs = sorted(o.plies + o.solved_plies, key=lambda r: r["turn"])
-        assert len(g["plies"]) == len(theirs)
-        for mine, ref in zip(g["plies"], theirs):
+        played = [p for p in g["plies"] if p["action"] >= 0]     # a resignation is logged as a ply with action -1, not as a record
+        assert len(played) == len(theirs)
+        assert len(g["plies"]) - len(played) == (1 if g["plies"][-1]["action"] < 0 else 0)   # at most one, and it is the last ply
+        for mine, ref in zip(played, theirs):
             assert (mine["own"], mine["enemy"], mine["pid"], mine["action"]) == (ref["own"], ref["enemy"], ref["pid"], ref["action"])
             assert mine["recorded"] == ("N" in ref)
             if "N" in ref:
@@ -255,6 +263,7 @@ def test_full_games_with_endgame_solver_exact(kw, budget_us, monkeypatch):
                 solved_total += 1
                 assert mine["n"] == 999.0 and mine["q"] == ref["q"]
         assert g["winner"] == o.env.winner and g["expansions"] == o.n_expand
+        assert g["resigned_mask"] == (1 if o.resigned[1] else 0) | (2 if o.resigned[2] else 0)
     if kw["use_solver_turn"]:
         assert solved_total > 0
 
