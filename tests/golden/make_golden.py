@@ -291,6 +291,57 @@ def gen_mcts_solver():
     return out
 
 
+def ref_selfplay_game_full(cfg, api, enable_resign):
+    """worker/self_play.py:139-175 + :219-238 driven directly, resignation included (action None -> env.step(None))."""
+    from reversi_zero.agent.player import CounterKey
+    env = ReversiEnv().reset()
+    info = ReversiPlayer.create_mtcs_info() if cfg.play.share_mtcs_info_in_self_play else None
+    players = {Player.black: ReversiPlayer(cfg, None, enable_resign=enable_resign, mtcs_info=info, api=api),
+               Player.white: ReversiPlayer(cfg, None, enable_resign=enable_resign, mtcs_info=info, api=api)}
+    plies = []
+    while not env.done:
+        pl = players[env.next_player]
+        own, enemy = (env.board.black, env.board.white) if env.next_player == Player.black else (env.board.white, env.board.black)
+        a = pl.action_with_evaluation(own, enemy)
+        n_now = pl.var_n[CounterKey(own, enemy, Player.black.value)]
+        plies.append(dict(pid=env.next_player.value, own=int(own), enemy=int(enemy), action=-1 if a.action is None else int(a.action),
+                          N=[int(x) for x in n_now], n=float(a.n), q=float(a.q)))
+        env.step(a.action)
+    z = {Winner.black: 1, Winner.white: -1, Winner.draw: 0}[env.winner]
+    players[Player.black].finish_game(z)
+    players[Player.white].finish_game(-z)
+    recs = [[[int(m[0][0]), int(m[0][1])], [float(x) for x in m[1]], int(m[2])] for m in players[Player.black].moves + players[Player.white].moves]
+    return plies, recs, z, dict(black=bool(players[Player.black].resigned), white=bool(players[Player.white].resigned)), int(env.turn)
+
+
+def gen_mcts_features():
+    """whole games of the reference player, K = 1, tau = 0, with the per-ply decision features on: rethinking loops
+    (agent/player.py:105-118), the resign rule (:123-130) with resignation enabled, separate tables, and all of them
+    together with the solver hooks."""
+    import hashlib
+    cases = {
+        "rethink_s12": dict(sims=12, share=True, play=dict(thinking_loop=3, required_visit_to_decide_action=40, start_rethinking_turn=2)),
+        "resign_s16": dict(sims=16, share=True, enable_resign=True, play=dict(resign_threshold=-0.4, allowed_resign_turn=10)),
+        "all_s20": dict(sims=20, share=False, enable_resign=True,
+                        play=dict(thinking_loop=2, required_visit_to_decide_action=30, start_rethinking_turn=2, resign_threshold=-0.5,
+                                  allowed_resign_turn=10, use_solver_turn=54, use_solver_turn_in_simulation=52)),
+        "all_no_resign_s20": dict(sims=20, share=False, enable_resign=False,
+                                  play=dict(thinking_loop=2, required_visit_to_decide_action=30, start_rethinking_turn=2, resign_threshold=-0.5,
+                                            allowed_resign_turn=10, use_solver_turn=54, use_solver_turn_in_simulation=52)),
+    }
+    out = {}
+    for name, c in cases.items():
+        api = FakeNet()
+        cfg = ref_config(sims=c["sims"], k=1, noise_eps=0, change_tau_turn=0, share=c["share"])
+        for k, v in c["play"].items():
+            setattr(cfg.play, k, v)
+        plies, recs, z, resigned, turn = ref_selfplay_game_full(cfg, api, c.get("enable_resign", False))
+        out[name] = dict(sims=c["sims"], share=c["share"], enable_resign=c.get("enable_resign", False), play=c["play"], plies=plies, z=z,
+                         resigned=resigned, turn=turn, n_records=len(recs),
+                         records_sha256=hashlib.sha256(json.dumps(recs).encode()).hexdigest(), expansions=api.rows)
+    return out
+
+
 def gen_ingest():
     """Trainer-side ingest: whole reference games -> the reference's own play_data file
     (lib/data_helper.py:23-25) -> its own loader + OptimizeWorker.convert_to_training_data (worker/optimize.py:215-231).
@@ -323,6 +374,11 @@ def gen_ingest():
 
 def main():
     import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "features":   # only (re)generate the decision-feature MCTS fixtures
+        with open(os.path.join(HERE, "mcts_features.json"), "w") as f:
+            json.dump(gen_mcts_features(), f)
+        print("mcts feature golden vectors written")
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "ingest":   # only (re)generate the trainer-ingest fixture
         np.savez_compressed(os.path.join(HERE, "ingest.npz"), **gen_ingest())
         print("ingest golden vectors written")
@@ -345,6 +401,8 @@ def main():
     with open(os.path.join(HERE, "mcts.json"), "w") as f:
         json.dump(mcts, f)
     np.savez_compressed(os.path.join(HERE, "ingest.npz"), **gen_ingest())
+    with open(os.path.join(HERE, "mcts_features.json"), "w") as f:
+        json.dump(gen_mcts_features(), f)
     print("golden vectors written to", HERE)
 
 

@@ -178,3 +178,32 @@ def test_mcts_with_solver_exact_vs_reference(golden_dir):
         recs = [[[int(o), int(e)], [float(x) for x in p], int(z)] for (o, e), p, z in game.records()]
         assert hashlib.sha256(json.dumps(recs).encode()).hexdigest() == ref["records_sha256"], name
         assert game.n_expand == ref["expansions"] and game.black_z == ref["z"]
+
+
+def test_mcts_decision_features_exact_vs_reference(golden_dir):
+    """whole games of the reference player with rethinking loops (agent/player.py:105-118), the resign rule (:123-130,
+    resignation enabled), separate tables and the solver hooks -- one at a time and all together (K = 1, tau = 0,
+    deterministic evaluator): every ply, every root visit vector, the resigned flags, the result, the training records
+    and the number of network evaluations equal the reference's."""
+    g = _load(golden_dir, "mcts_features.json")
+    for name, ref in g.items():
+        kw = dict(simulation_num_per_move=ref["sims"], parallel_search_num=1, noise_eps=0.0, change_tau_turn=0, c_puct=5, thinking_loop=1,
+                  resign_threshold=None, share_mtcs_info_in_self_play=ref["share"], use_solver_turn=0, use_solver_turn_in_simulation=0)
+        kw.update(ref["play"])
+        game = mcts.SelfPlayGame(mcts.PlayParams(**kw), nn.FakeNetAPI(), seed=7, game_id=0)
+        game.enable_resign = ref["enable_resign"]      # the reference decides this per game with random() (self_play.py:144)
+        game.play()
+        mine = sorted(game.plies + game.solved_plies, key=lambda r: r["turn"])
+        theirs = [p for p in ref["plies"] if p["action"] >= 0]
+        assert len(mine) == len(theirs), name
+        assert len(ref["plies"]) - len(theirs) == (1 if game.actions[-1] is None else 0), name      # the resignation itself
+        for a, b in zip(mine, theirs):
+            assert (a["pid"], a["own"], a["enemy"], a["action"]) == (b["pid"], b["own"], b["enemy"], b["action"]), (name, a["turn"])
+            if "N" in a:
+                assert list(a["N"]) == b["N"], (name, a["turn"])       # includes the visits of every rethinking loop
+            assert abs(a["q"] - b["q"]) < 1e-6 and a["n"] == b["n"], (name, a["turn"])
+        assert (game.resigned[1], game.resigned[2]) == (ref["resigned"]["black"], ref["resigned"]["white"]), name
+        assert game.black_z == ref["z"] and game.env.turn == ref["turn"], name
+        recs = [[[int(o), int(e)], [float(x) for x in p], int(z)] for (o, e), p, z in game.records()]
+        assert len(recs) == ref["n_records"] and hashlib.sha256(json.dumps(recs).encode()).hexdigest() == ref["records_sha256"], name
+        assert game.n_expand == ref["expansions"], name
