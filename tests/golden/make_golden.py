@@ -291,11 +291,13 @@ def gen_mcts_solver():
     return out
 
 
-def ref_selfplay_game_full(cfg, api, enable_resign):
-    """worker/self_play.py:139-175 + :219-238 driven directly, resignation included (action None -> env.step(None))."""
+def ref_selfplay_game_full(cfg, api, enable_resign, info=None):
+    """worker/self_play.py:139-175 + :219-238 driven directly, resignation included (action None -> env.step(None)).
+    ``info``: an MCTSInfo kept from earlier games (reset_mtcs_info_per_game > 1, worker/self_play.py:108-134)."""
     from reversi_zero.agent.player import CounterKey
     env = ReversiEnv().reset()
-    info = ReversiPlayer.create_mtcs_info() if cfg.play.share_mtcs_info_in_self_play else None
+    if info is None:
+        info = ReversiPlayer.create_mtcs_info() if cfg.play.share_mtcs_info_in_self_play else None
     players = {Player.black: ReversiPlayer(cfg, None, enable_resign=enable_resign, mtcs_info=info, api=api),
                Player.white: ReversiPlayer(cfg, None, enable_resign=enable_resign, mtcs_info=info, api=api)}
     plies = []
@@ -339,6 +341,17 @@ def gen_mcts_features():
         out[name] = dict(sims=c["sims"], share=c["share"], enable_resign=c.get("enable_resign", False), play=c["play"], plies=plies, z=z,
                          resigned=resigned, turn=turn, n_records=len(recs),
                          records_sha256=hashlib.sha256(json.dumps(recs).encode()).hexdigest(), expansions=api.rows)
+    # reset_mtcs_info_per_game = 3 (config/mini.yml:13): three consecutive games on ONE MCTSInfo; new players start with
+    # expanded = set(var_p.keys()) (agent/player.py:44-47)
+    cfg = ref_config(sims=14, k=1, noise_eps=0, change_tau_turn=0, share=True)
+    info = ReversiPlayer.create_mtcs_info()
+    games = []
+    for _ in range(3):
+        api = FakeNet()
+        plies, recs, z, resigned, turn = ref_selfplay_game_full(cfg, api, False, info=info)
+        games.append(dict(plies=plies, z=z, turn=turn, n_records=len(recs), records_sha256=hashlib.sha256(json.dumps(recs).encode()).hexdigest(),
+                          expansions=api.rows))
+    out["kept_table_3_games_s14"] = dict(sims=14, games=games, table_size=len(info.var_p))
     return out
 
 
