@@ -6,8 +6,8 @@ The reference plays the games one after the other with two in-process ``ReversiP
 a match run concurrently on the device (``rz_engine_set_second_net``): each search is evaluated by the mover's own
 network, colours alternate by game index (the reference draws them at random, :70), each player keeps its own
 statistics (``share_mtcs_info = 0``, as ``ReversiPlayer(config, model, play_config=...)`` does in :69-70).  The
-early-stop rules (:56-61) only shorten a sequential match; with concurrent games the verdict is computed from all
-finished games.  Weights are exchanged as float32 blobs (``*.rzblob.npy``)."""
+verdict follows the reference's sequential bookkeeping (:44-64) over the games in game-index order, including its
+early-stop rules -- games after the point where the reference would have stopped do not count.  Weights are exchanged as float32 blobs (``*.rzblob.npy``)."""
 import os
 import shutil
 from glob import glob
@@ -73,6 +73,24 @@ def play_match(config, best_net, ng_net, game_num, device=0, seed=0):
     return results, games
 
 
+def match_verdict(results, game_num, replace_rate):
+    """worker/evaluate.py:44-64 replayed over ``results`` (game-index order; 1 challenger won, 0 lost, None draw):
+    returns (replace: bool, winning_rate, games_counted).  The reference stops as soon as the losses reach
+    game_num * (1 - replace_rate) or the wins reach game_num * replace_rate, and then decides on the winning rate so far."""
+    decided = []
+    counted = 0
+    for r in results[:game_num]:
+        counted += 1
+        if r is not None:
+            decided.append(r)
+        if decided.count(0) >= game_num * (1 - replace_rate):
+            break
+        if decided.count(1) >= game_num * replace_rate:
+            break
+    winning_rate = sum(decided) / len(decided) if decided else 0.0   # the reference divides by zero when every game is a draw
+    return winning_rate >= replace_rate, winning_rate, counted
+
+
 class EvaluateWorker:
     def __init__(self, config, device=0):
         self.config = config
@@ -99,10 +117,9 @@ class EvaluateWorker:
         game_num = int(_eval_field(self.config, "game_num", 200))
         replace_rate = float(_eval_field(self.config, "replace_rate", 0.55))
         results, _ = play_match(self.config, self.best_net, ng_net, game_num, self.device)
-        decided = [r for r in results if r is not None]
-        winning_rate = sum(decided) / len(decided) if decided else 0.0
-        logger.debug(f"winning rate {winning_rate * 100:.1f}% over {len(decided)} decided games")
-        return winning_rate >= replace_rate
+        replace, winning_rate, counted = match_verdict(results, game_num, replace_rate)
+        logger.debug(f"winning rate {winning_rate * 100:.1f}% after {counted} games")
+        return replace
 
     def next_generation_dir(self):
         rc = self.config.resource

@@ -144,3 +144,33 @@ def test_weight_source_selection(tmp_path):
     assert sp.weight_source_path(cfg) == best
     os.remove(best)
     assert sp.weight_source_path(cfg) == newest                   # load_best_model_weight(...) or reload_newest_...(...)
+
+
+def test_match_verdict_follows_the_sequential_reference():
+    """worker/evaluate.py:44-64, restated literally here as the check: sequential bookkeeping with both early-stop rules."""
+    from reversi_zero_b200.worker.evaluate import match_verdict
+
+    def reference(results, game_num, replace_rate):
+        seq, rate = [], 0
+        for ng_win in results[:game_num]:
+            if ng_win is not None:
+                seq.append(ng_win)
+                rate = sum(seq) / len(seq)
+            if seq.count(0) >= game_num * (1 - replace_rate):
+                break
+            if seq.count(1) >= game_num * replace_rate:
+                break
+        rate = sum(seq) / len(seq)
+        return rate >= replace_rate
+
+    rng = np.random.default_rng(1)
+    for game_num, rr in ((200, 0.55), (10, 0.55), (7, 0.5), (20, 0.6)):
+        for p_win in (0.3, 0.5, 0.55, 0.6, 0.8):
+            for _ in range(40):
+                res = [None if u < 0.05 else int(u < 0.05 + 0.95 * p_win) for u in rng.random(game_num)]
+                if all(r is None for r in res):
+                    continue
+                assert match_verdict(res, game_num, rr)[0] == reference(res, game_num, rr)
+    # the early stop matters: 6 wins out of the first 6 games of 10 end the match although the rest are losses
+    assert match_verdict([1] * 6 + [0] * 4, 10, 0.55) == (True, 1.0, 6)
+    assert match_verdict([0] * 5 + [1] * 5, 10, 0.55) == (False, 0.0, 5)
