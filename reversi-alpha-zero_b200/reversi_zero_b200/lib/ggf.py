@@ -17,7 +17,7 @@ def convert_move_to_action(move_str):
 
 
 def make_ggf_string(black_name=None, white_name=None, dt=None, moves=None, result=None, think_time_sec=60):
-    dt = dt or datetime.now(timezone.utc)
+    dt = dt or datetime.now(timezone.utc).replace(tzinfo=None)  # the reference's naive datetime.utcnow(): "%Z" prints nothing
     body = "".join(f"{'B' if i % 2 == 0 else 'W'}[{m}]" for i, m in enumerate(moves or []))
     return ("(;GM[Othello]PC[RAZSelf]DT[%s]PB[%s]PW[%s]RE[%s]TI[%d:%d]TY[8]"
             "BO[8 ---------------------------O*------*O--------------------------- *]%s;)") % (

@@ -174,3 +174,43 @@ def test_match_verdict_follows_the_sequential_reference():
     # the early stop matters: 6 wins out of the first 6 games of 10 end the match although the rest are losses
     assert match_verdict([1] * 6 + [0] * 4, 10, 0.55) == (True, 1.0, 6)
     assert match_verdict([0] * 5 + [1] * 5, 10, 0.55) == (False, 0.0, 5)
+
+
+def test_ggf_text_matches_reference_module(tmp_path):
+    """lib/ggf.py of the reference (importable as it is: stdlib only) against the mirror: square names both ways, the
+    record line for a fixed date, and MoveHistory's pass insertion (worker/self_play.py:275-299) against the worker's
+    _ggf_of.  Runs where the reference checkout exists."""
+    import oracle.ref_shims.install as shims
+    if not shims.available():
+        pytest.skip("reference sources not present")
+    shims.install()
+    from datetime import datetime
+    from reversi_zero.lib import ggf as ref
+    from reversi_zero_b200.lib import ggf as mine
+    for a in list(range(64)) + [None]:
+        mv = ref.convert_action_to_move(a)
+        assert mine.convert_action_to_move(a) == mv and mine.convert_move_to_action(mv) == ref.convert_move_to_action(mv) == a
+    assert mine.convert_move_to_action("f5") == ref.convert_move_to_action("f5") == 44      # test/lib/test_ggf.py:32-43
+    dt = datetime(2026, 9, 22, 13, 5, 9)
+    moves = ["C4/2.5/10.0", "C3/-5.0/7.0", "PA", "C2/0.0/3.0"]
+    for kw in (dict(), dict(result="+12.0", think_time_sec=125)):
+        assert mine.make_ggf_string("RAZ", "RAZ", dt=dt, moves=moves, **kw) == ref.make_ggf_string("RAZ", "RAZ", dt=dt, moves=moves, **kw)
+    assert mine.make_ggf_string(dt=dt) == ref.make_ggf_string(dt=dt)
+    # without dt both stamp "now" (UTC, naive): same layout, the "%Z" part empty
+    assert mine.make_ggf_string()[: len("(;GM[Othello]PC[RAZSelf]DT[")] == ref.make_ggf_string()[: len("(;GM[Othello]PC[RAZSelf]DT[")]
+    assert mine.make_ggf_string().split("DT[")[1].split("]")[0].endswith(".") and ref.make_ggf_string().split("DT[")[1].split("]")[0].endswith(".")
+    # MoveHistory: black C4, white C3, white again (black had to pass), black resigns
+    from reversi_zero.worker.self_play import MoveHistory
+    from reversi_zero.agent.player import ActionWithEvaluation
+    from reversi_zero.env.reversi_env import Player
+    mh = MoveHistory()
+    P = _cabi.Ply
+    plies = []
+    for action, player, q, n in ((19, 1, 0.25, 10.0), (18, 2, -0.5, 7.0), (17, 2, 0.0, 3.0), (-1, 1, 0.0, 0.0)):
+        env = types.SimpleNamespace(next_player=Player.black if player == 1 else Player.white)
+        mh.move(env, ActionWithEvaluation(None if action < 0 else action, n, q))
+        p = P(); p.action, p.player, p.q, p.n = action, player, q, n
+        plies.append(p)
+    cfg, w = make_worker(tmp_path)
+    theirs, ours = mh.make_ggf_string("RAZ", "RAZ"), w._ggf_of(None, plies)
+    assert theirs.split("BO[")[1] == ours.split("BO[")[1]            # everything after the date stamp
