@@ -214,3 +214,52 @@ def test_ggf_text_matches_reference_module(tmp_path):
     cfg, w = make_worker(tmp_path)
     theirs, ours = mh.make_ggf_string("RAZ", "RAZ"), w._ggf_of(None, plies)
     assert theirs.split("BO[")[1] == ours.split("BO[")[1]            # everything after the date stamp
+
+
+def test_resign_tuner_and_schedule_match_reference_worker(tmp_path):
+    """The UNMODIFIED reference SelfPlayWorker.finish_game / check_and_update_resignation_threshold /
+    decide_simulation_num_per_move (worker/self_play.py:219-272), called as plain functions on a stand-in `self`, against
+    the mirror over random game sequences.  Runs where the reference checkout exists."""
+    import oracle.ref_shims.install as shims
+    if not shims.available():
+        pytest.skip("reference sources not present")
+    shims.install()
+    from reversi_zero.worker.self_play import SelfPlayWorker as Ref
+    from reversi_zero.env.reversi_env import Winner
+    cfg, w = make_worker(tmp_path)
+    cfg.play.resign_threshold, cfg.play.false_positive_threshold, cfg.play.resign_threshold_delta = -0.8, 0.05, 0.01
+
+    class RefSelf:     # what the reference methods touch
+        pass
+    r = RefSelf()
+    r.config = types.SimpleNamespace(play=types.SimpleNamespace(resign_threshold=-0.8, false_positive_threshold=0.05, resign_threshold_delta=0.01,
+                                                                 schedule_of_simulation_num_per_move=[(0, 8), (300, 50), (2000, 200)]),
+                                     resource=types.SimpleNamespace(force_simulation_num_file=str(tmp_path / "ref_force_sim")))
+    r.resign_test_game_count = r.false_positive_count_of_resign = 0
+    r.check_and_update_resignation_threshold = lambda: Ref.check_and_update_resignation_threshold(r)
+    r.reset_false_positive_count = lambda: Ref.reset_false_positive_count(r)
+    type(r).false_positive_rate = Ref.false_positive_rate
+    rng = np.random.default_rng(9)
+    winners = {1: Winner.black, 2: Winner.white, 3: Winner.draw}
+    for i in range(1500):
+        winner = int(rng.integers(1, 4))
+        mask = int(rng.integers(0, 4)) if rng.random() < 0.2 else 0
+        enabled = bool(rng.random() < 0.4)
+        player = lambda bit: types.SimpleNamespace(resigned=bool(mask & bit), finish_game=lambda z: None)   # noqa: E731
+        r.env = types.SimpleNamespace(winner=winners[winner])
+        r.black, r.white = player(1), player(2)
+        Ref.finish_game(r, resign_enabled=enabled)
+        w._finish_game(game(winner=winner, resigned_mask=mask, resign_enabled=int(enabled)))
+        assert abs(cfg.play.resign_threshold - r.config.play.resign_threshold) < 1e-12, i
+        assert (w.resign_test_game_count, w.false_positive_count_of_resign) == (r.resign_test_game_count, r.false_positive_count_of_resign), i
+    assert abs(cfg.play.resign_threshold - (-0.8)) > 0.005          # the threshold did move during the sequence
+    # schedule + .force-sim override
+    cfg.play.schedule_of_simulation_num_per_move = [[0, 8], [300, 50], [2000, 200]]
+    for idx in (0, 1, 299, 300, 301, 1999, 2000, 123456):
+        assert w.decide_simulation_num_per_move(idx) == Ref.decide_simulation_num_per_move(r, idx)
+    for text in ("77\n", "0", "abc", ""):
+        for path in (cfg.resource.force_simulation_num_file, r.config.resource.force_simulation_num_file):
+            with open(path, "wt") as f:
+                f.write(text)
+        for idx in (0, 5000):
+            assert w.decide_simulation_num_per_move(idx) == Ref.decide_simulation_num_per_move(r, idx), (text, idx)
