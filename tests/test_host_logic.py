@@ -263,3 +263,44 @@ def test_resign_tuner_and_schedule_match_reference_worker(tmp_path):
                 f.write(text)
         for idx in (0, 5000):
             assert w.decide_simulation_num_per_move(idx) == Ref.decide_simulation_num_per_move(r, idx), (text, idx)
+
+
+def test_config_mirror_matches_reference_defaults_and_yaml():
+    """Every attribute of the reference's Config() sections this path reads (config.py: resource paths relative to the
+    project dir, model, play, play_data) has the same default in the mirror, and the reference's own config/*.yml files
+    overlay to the same values through both loaders.  Runs where the reference checkout exists."""
+    import oracle.ref_shims.install as shims
+    if not shims.available():
+        pytest.skip("reference sources not present")
+    shims.install()
+    import yaml
+    from moke_config import create_config as ref_create
+    from reversi_zero.config import Config as RefConfig
+    from reversi_zero_b200.config import load_yaml
+
+    def plain(v):
+        return [plain(x) for x in v] if isinstance(v, (list, tuple)) else v
+
+    def compare(ref, mine, sections):
+        for sec in sections:
+            rs, ms = getattr(ref, sec), getattr(mine, sec)
+            for k, v in vars(rs).items():
+                if sec == "resource":
+                    if isinstance(v, str) and os.sep in v:        # absolute paths: compare relative to the project dir
+                        assert os.path.relpath(getattr(ms, k), mine.resource.project_dir) == os.path.relpath(v, ref.resource.project_dir), k
+                    elif not isinstance(v, str):
+                        continue
+                    else:
+                        assert getattr(ms, k) == v, k
+                else:
+                    assert plain(getattr(ms, k)) == plain(v), (sec, k)
+
+    compare(RefConfig(), Config(project_dir="/tmp/rz_proj"), ("resource", "model", "play", "play_data"))
+    cfg_dir = "/root/reference/config"
+    for name in sorted(os.listdir(cfg_dir)):
+        if not name.endswith(".yml"):
+            continue
+        with open(os.path.join(cfg_dir, name), "rt") as f:
+            ref = ref_create(RefConfig, yaml.safe_load(f))
+        mine = load_yaml(os.path.join(cfg_dir, name), project_dir="/tmp/rz_proj")
+        compare(ref, mine, ("model", "play", "play_data"))
