@@ -294,3 +294,48 @@ def test_reset_mtcs_info_per_game():
                    [(p["own"], p["enemy"], p["action"], list(p["N"])) for p in o.plies], gid
             assert g["expansions"] == o.n_expand
     assert st["max_nodes_used"] > 0
+
+
+def test_full_size_selfplay_properties_and_sampled_exactness():
+    """BASELINE config-2 shape -- 4096 resident games, 400 simulations per move, K = 8, Dirichlet noise, two slot groups --
+    with the deterministic evaluator, every game played from the first to the last ply.  Size-independent properties
+    over ALL games (ids, results, visit accounting, legality) + replay parity and EXACT equality with the oracle for a
+    sample of game ids (a game's content depends only on (seed, game id), not on the 4095 games around it)."""
+    pp = params(simulation_num_per_move=400, parallel_search_num=8)
+    G = 4096
+    eng = make_engine(pp, games=G, seed=20260922, max_games=G, overlap_groups=2, max_searches_per_game=60)
+    eng.run(finished_target=G)
+    games = eng.poll()
+    st = eng.stats()
+    eng.close()
+    assert sorted(g["game_id"] for g in games) == list(range(G))                       # every id exactly once
+    assert st["games_finished"] == G and st["expansions"] == sum(g["expansions"] for g in games)
+    n_plies = 0
+    for g in games:
+        assert g["winner"] in (1, 2, 3) and g["black_z"] == {1: 1, 2: -1, 3: 0}[g["winner"]]
+        nb, nw = bin(g["black"]).count("1"), bin(g["white"]).count("1")
+        assert g["winner"] == (1 if nb > nw else 2 if nw > nb else 3) and not (g["black"] & g["white"])   # no resignation in this config
+        for p in g["plies"]:
+            n_plies += 1
+            N = np.asarray(p["N"])
+            legal = ob.find_correct_moves(p["own"], p["enemy"])
+            turn = bin(p["own"] | p["enemy"]).count("1") - 4
+            if turn == 0:
+                continue                                                                 # first move is forced without a search (player.py:143-148)
+            assert all((legal >> int(a)) & 1 for a in np.nonzero(N)[0]) and (legal >> p["action"]) & 1
+            assert N.sum() >= 400 - 1 and N[p["action"]] > 0                              # this search's simulations (+ visits kept from earlier plies)
+    assert 59 * G <= n_plies <= 61 * G
+    exp = np.array([g["expansions"] for g in games])
+    assert 20000 < exp.mean() < 22500                                                    # survey probe of the reference: ~21.3 k per game at S = 400
+    by_id = {g["game_id"]: g for g in games}
+    for gid in (0, 1234, 2047, 2048, 4095):                                             # both slot groups, first / last slots
+        g = by_id[gid]
+        replay_check(g)
+        o = mcts.SelfPlayGame(pp, onn.FakeNetAPI(), seed=20260922, game_id=gid).play()
+        assert len(g["plies"]) == len(o.plies)
+        for mine, theirs in zip(g["plies"], o.plies):
+            assert (mine["own"], mine["enemy"], mine["pid"], mine["action"]) == (theirs["own"], theirs["enemy"], theirs["pid"], theirs["action"])
+            assert list(mine["N"]) == list(theirs["N"])
+        assert g["winner"] == o.env.winner and g["expansions"] == o.n_expand
+    for g in games[::64]:
+        replay_check(g)
