@@ -59,9 +59,16 @@ def load_or_build_weights(config, net):
     newest next-generation weights, else -- or if there are none -- the best weights; nothing there (or ``--new``):
     build() + save_as_best.  The engine-side hand-off files are float32 .npy blobs."""
     path = None if getattr(config.opts, "new", False) else weight_source_path(config)
+    h5_path = None if (path is not None or getattr(config.opts, "new", False)) else keras_h5_source_path(config)
     if path is not None:
         blob = np.load(path)
         logger.debug(f"loading weights from {path}")
+    elif h5_path is not None:
+        # no exported blob, but the trainer's own h5 file is there: read it directly (lib/h5lite.py -- unpinned reader, it
+        # raises on anything it does not understand rather than guessing)
+        from ..lib.h5lite import blob_from_keras_h5
+        blob = blob_from_keras_h5(config.model, h5_path)
+        logger.info(f"loaded Keras weights from {h5_path}")
     else:
         path = blob_path_of(config)
         blob = M.weights_to_blob(config.model, M.build_random_weights(config.model, _b200(config).weight_seed))
@@ -87,6 +94,24 @@ def newest_next_generation_blob(config):
         path = os.path.join(d, NEXT_GENERATION_BLOB)
         return path if os.path.exists(path) else None   # only the newest directory counts, like the reference
     return None
+
+
+def keras_h5_source_path(config):
+    """The reference's own weight files (config.py:30-40), same newest-first / best-first rule as weight_source_path."""
+    from glob import glob
+    rc = config.resource
+    best = getattr(rc, "model_best_weight_path", os.path.join(rc.model_dir, "model_best_weight.h5"))
+    best = best if os.path.exists(best) else None
+    base = getattr(rc, "next_generation_model_dir", os.path.join(rc.model_dir, "next_generation"))
+    tmpl = getattr(rc, "next_generation_model_dirname_tmpl", "model_%s")
+    newest = None
+    for d in reversed(sorted(glob(os.path.join(base, tmpl % "*")))):
+        cand = os.path.join(d, getattr(rc, "next_generation_model_weight_filename", "model_weight.h5"))
+        newest = cand if os.path.exists(cand) else None
+        break
+    if getattr(config.play, "use_newest_next_generation_model", True):
+        return newest or best
+    return best or newest
 
 
 def weight_source_path(config):
