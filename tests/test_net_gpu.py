@@ -94,6 +94,12 @@ def test_tcgen05_ch5_vs_oracle(n):
     run_case(M.ModelConfig(**CH5), n, N.IMPL_TCGEN05, seed=0, perturb=False, tol=1e-3)
 
 
+def test_tcgen05_deep_tower_config4():
+    """BASELINE config 4: the same kernel with a deeper tower (19 residual blocks = 39 convolutions, the AlphaGo Zero
+    depth), random-init as `--new` builds it; same 1e-3 bound on policy probabilities and value."""
+    run_case(M.ModelConfig(cnn_filter_num=256, res_layer_num=19, value_fc_size=256), 96, N.IMPL_TCGEN05, seed=0, perturb=False, tol=1e-3)
+
+
 def test_tcgen05_ch5_perturbed_bn_and_value_fc():
     """stress case, NOT the north-star configuration: random biases and BN statistics (gamma 0.5-1.5, var 0.5-2)
     compound over 21 layers into activations ~10x larger than with `--new` weights, which amplifies the fp16
