@@ -352,6 +352,19 @@ def gen_mcts_features():
         games.append(dict(plies=plies, z=z, turn=turn, n_records=len(recs), records_sha256=hashlib.sha256(json.dumps(recs).encode()).hexdigest(),
                           expansions=api.rows))
     out["kept_table_3_games_s14"] = dict(sims=14, games=games, table_size=len(info.var_p))
+    # the same with the solver hooks on (config/mini.yml: reset_mtcs_info_per_game 3 AND use_solver_turn* 50): every game
+    # has fresh ReversiSolver objects (agent/player.py:60) but meets the priors / visits earlier solves left in the table
+    cfg = ref_config(sims=14, k=1, noise_eps=0, change_tau_turn=0, share=True)
+    cfg.play.use_solver_turn, cfg.play.use_solver_turn_in_simulation = 54, 51
+    info = ReversiPlayer.create_mtcs_info()
+    games = []
+    for _ in range(3):
+        api = FakeNet()
+        plies, recs, z, resigned, turn = ref_selfplay_game_full(cfg, api, False, info=info)
+        games.append(dict(plies=plies, z=z, turn=turn, n_records=len(recs), records_sha256=hashlib.sha256(json.dumps(recs).encode()).hexdigest(),
+                          expansions=api.rows))
+    out["kept_table_solver_3_games_s14"] = dict(sims=14, use_solver_turn=54, use_solver_turn_in_simulation=51, games=games,
+                                                table_size=len(info.var_p))
     return out
 
 

@@ -268,10 +268,12 @@ def test_full_games_with_endgame_solver_exact(kw, budget_us, monkeypatch):
         assert solved_total > 0
 
 
-def test_reset_mtcs_info_per_game():
+@pytest.mark.parametrize("solver", [False, True])
+def test_reset_mtcs_info_per_game(solver):
     """PlayConfig.reset_mtcs_info_per_game = 3 (config/mini.yml:13): a slot keeps its statistics across three consecutive
-    games (worker/self_play.py:111-134); whole games equal the oracle that is handed the previous game's table."""
-    pp = params(simulation_num_per_move=20, change_tau_turn=0)
+    games (worker/self_play.py:111-134); whole games equal the oracle that is handed the previous game's table -- also
+    with the solver hooks on, as mini.yml has them (solved positions of earlier games are met again in the kept table)."""
+    pp = params(simulation_num_per_move=20, change_tau_turn=0, **(dict(use_solver_turn=54, use_solver_turn_in_simulation=51) if solver else {}))
     pp.reset_mtcs_info_per_game = 3
     n_games = 8  # 2 slots x 4 games: games 0,2,4 / 1,3,5 share a table, games 6 / 7 start a new one
     eng = make_engine(pp, games=2, seed=61, max_games=n_games)
@@ -290,9 +292,10 @@ def test_reset_mtcs_info_per_game():
             table = o.table
             g = games[gid]
             replay_check(g)
-            assert [(p["own"], p["enemy"], p["action"], list(p["N"])) for p in g["plies"]] == \
-                   [(p["own"], p["enemy"], p["action"], list(p["N"])) for p in o.plies], gid
-            assert g["expansions"] == o.n_expand
+            theirs = sorted(o.plies + o.solved_plies, key=lambda r: r["turn"])
+            assert [(p["own"], p["enemy"], p["action"], list(p["N"]) if p["recorded"] else None) for p in g["plies"]] == \
+                   [(p["own"], p["enemy"], p["action"], list(p["N"]) if "N" in p else None) for p in theirs], gid
+            assert g["expansions"] == o.n_expand and g["winner"] == o.env.winner
     assert st["max_nodes_used"] > 0
 
 

@@ -214,18 +214,25 @@ def test_mcts_decision_features_exact_vs_reference(golden_dir):
 def test_mcts_kept_table_exact_vs_reference(golden_dir):
     """reset_mtcs_info_per_game = 3 (worker/self_play.py:108-134): three consecutive reference games on ONE MCTSInfo; the
     oracle is handed the previous game's table and must reproduce games 2 and 3 as well."""
-    ref = _load(golden_dir, "mcts_features.json")["kept_table_3_games_s14"]
+    for name in ("kept_table_3_games_s14", "kept_table_solver_3_games_s14"):
+        _check_kept_table_games(_load(golden_dir, "mcts_features.json")[name], name)
+
+
+def _check_kept_table_games(ref, name):
     pp = mcts.PlayParams(simulation_num_per_move=ref["sims"], parallel_search_num=1, noise_eps=0.0, change_tau_turn=0, c_puct=5, thinking_loop=1,
-                         resign_threshold=None, share_mtcs_info_in_self_play=True, reset_mtcs_info_per_game=3)
+                         resign_threshold=None, share_mtcs_info_in_self_play=True, reset_mtcs_info_per_game=3,
+                         use_solver_turn=ref.get("use_solver_turn", 0), use_solver_turn_in_simulation=ref.get("use_solver_turn_in_simulation", 0))
     table = None
     for i, rg in enumerate(ref["games"]):
         game = mcts.SelfPlayGame(pp, nn.FakeNetAPI(), seed=7, game_id=i, table=table).play()
         table = game.table
-        assert len(game.plies) == len(rg["plies"]), i
-        for a, b in zip(game.plies, rg["plies"]):
-            assert (a["pid"], a["own"], a["enemy"], a["action"]) == (b["pid"], b["own"], b["enemy"], b["action"]), (i, a["turn"])
-            assert list(a["N"]) == b["N"], (i, a["turn"])
-            assert abs(a["q"] - b["q"]) < 1e-6 and a["n"] == b["n"], (i, a["turn"])
+        mine = sorted(game.plies + game.solved_plies, key=lambda r: r["turn"])
+        assert len(mine) == len(rg["plies"]), (name, i)
+        for a, b in zip(mine, rg["plies"]):
+            assert (a["pid"], a["own"], a["enemy"], a["action"]) == (b["pid"], b["own"], b["enemy"], b["action"]), (name, i, a["turn"])
+            if "N" in a:
+                assert list(a["N"]) == b["N"], (name, i, a["turn"])
+            assert abs(a["q"] - b["q"]) < 1e-6 and a["n"] == b["n"], (name, i, a["turn"])
         recs = [[[int(o), int(e)], [float(x) for x in p], int(z)] for (o, e), p, z in game.records()]
         assert hashlib.sha256(json.dumps(recs).encode()).hexdigest() == rg["records_sha256"], i
         assert game.n_expand == rg["expansions"] and game.black_z == rg["z"] and game.env.turn == rg["turn"], i
