@@ -11,6 +11,7 @@ Self-play does NOT go through this class -- thousands of games are played concur
 """
 from collections import namedtuple
 from logging import getLogger
+from types import SimpleNamespace
 
 import numpy as np
 
@@ -35,7 +36,14 @@ class ReversiPlayer:
         self.play_config = play_config or self.config.play
         self.enable_resign = enable_resign
         self.api = api
-        ecfg = engine_cfg_from_play_config(self.play_config, games=1, seed=seed,
+        # The reference reads three search parameters from config.play even when a separate play_config is given
+        # (evaluate.py / play_game callers): allowed_resign_turn (agent/player.py:127, handled below),
+        # use_solver_turn_in_simulation (:237-238) and virtual_loss (:264).
+        search_pc = SimpleNamespace(**vars(self.play_config))
+        for k in ("use_solver_turn_in_simulation", "virtual_loss"):
+            if hasattr(self.config.play, k):
+                setattr(search_pc, k, getattr(self.config.play, k))
+        ecfg = engine_cfg_from_play_config(search_pc, games=1, seed=seed,
                                            eval_mode=EVAL_NET if model is not None else EVAL_FAKE)
         self.engine = Engine(ecfg, model, device)
         self._fresh = True
@@ -77,7 +85,8 @@ class ReversiPlayer:
         return n.astype(np.float64), w.astype(np.float64)
 
     def action_with_evaluation(self, own, enemy, callback_in_mtcs=None):
-        """agent/player.py:82-134 (solver hooks excluded: SURVEY 8(f).2)."""
+        """agent/player.py:82-134; the exact root solver (:100-103,150-161) runs through lib/reversi_solver (rz_solve), the
+        WLD solver inside simulations (:237-251) inside the engine."""
         pc = self.play_config
         turn = bit_count(own) + bit_count(enemy) - 4
         self.callback_in_mtcs = callback_in_mtcs

@@ -31,15 +31,30 @@ def start(config):
 
 
 def eval_play_config(config):
-    """EvaluateConfig.play_config defaults (config.py:103-113) over the self-play PlayConfig, or the
-    ``eval.play_config`` mapping of a YAML file."""
-    pc = SimpleNamespace(**vars(config.play))
-    over = dict(simulation_num_per_move=400, thinking_loop=1, change_tau_turn=0, noise_eps=0, disable_resignation_rate=0)
+    """The play configuration an evaluation game really runs with in the reference:
+
+    * ``EvaluateConfig.play_config`` is a FRESH ``PlayConfig()`` -- the defaults, not a copy of the self-play section --
+      with five overrides (config.py:103-113), overlaid with the ``eval.play_config`` mapping of a YAML file (mini.yml and
+      alpha_go_zero.yml merge their ``play`` section into it with a YAML anchor; ch5.yml has no eval section, so e.g.
+      ``c_puct`` is the default 1 there and the exact root solver is on from turn 50);
+    * three fields are read from the SELF-PLAY section even in evaluation games, because ``ReversiPlayer`` uses
+      ``self.config.play`` for them: ``allowed_resign_turn`` (agent/player.py:127), ``use_solver_turn_in_simulation``
+      (:237-238) and ``virtual_loss`` (:264);
+    * the two players never share statistics (``ReversiPlayer(config, model, play_config=...)``, worker/evaluate.py:69-70).
+    """
+    from ..config import PlayConfig
     ev = getattr(config, "eval", None)
     user = (ev.get("play_config") if isinstance(ev, dict) else getattr(ev, "play_config", None)) or {}
-    over.update(user if isinstance(user, dict) else vars(user))
-    for k, v in over.items():
-        setattr(pc, k, v)
+    if not isinstance(user, dict) and all(hasattr(user, k) for k in ("simulation_num_per_move", "c_puct", "thinking_loop")):
+        pc = SimpleNamespace(**vars(user))       # a complete PlayConfig object (the reference's own Config): use it as it is
+    else:
+        pc = SimpleNamespace(**vars(PlayConfig()))
+        over = dict(simulation_num_per_move=400, thinking_loop=1, change_tau_turn=0, noise_eps=0, disable_resignation_rate=0)
+        over.update(user if isinstance(user, dict) else vars(user))
+        for k, v in over.items():
+            setattr(pc, k, v)
+    for k in ("allowed_resign_turn", "use_solver_turn_in_simulation", "virtual_loss"):
+        setattr(pc, k, getattr(config.play, k))
     pc.share_mtcs_info_in_self_play = False
     return pc
 

@@ -368,6 +368,63 @@ def gen_mcts_features():
     return out
 
 
+def gen_eval_match():
+    """The UNMODIFIED EvaluateWorker.play_game (worker/evaluate.py:66-96) with two different deterministic evaluators
+    behind the reference's own ReversiModelAPI (agent/api.py:30-45): best = FakeNet, challenger = FakeNet with the value
+    negated.  The players are the reference's ReversiPlayer, wrapped only to log what they were asked and answered."""
+    import types
+    import reversi_zero.worker.evaluate as ev
+    from reversi_zero.agent.player import CounterKey
+
+    def model(sign):
+        def predict_on_batch(x):
+            p, v = FakeNet().predict(x)
+            return p, v * np.float32(sign)
+        return types.SimpleNamespace(model=types.SimpleNamespace(predict_on_batch=predict_on_batch))
+
+    log = []
+
+    class LoggingPlayer(ReversiPlayer):
+        def action(self, own, enemy, callback_in_mtcs=None):
+            a = super().action(own, enemy, callback_in_mtcs)
+            n = self.var_n[CounterKey(own, enemy, Player.black.value)]
+            log.append(dict(own=int(own), enemy=int(enemy), action=-1 if a is None else int(a), N=[int(x) for x in n],
+                            resigned=bool(self.resigned)))
+            return a
+
+    out = {}
+    real_player, real_random = ev.ReversiPlayer, ev.random
+    # "default_solver": the solver settings an evaluation game has when nobody touches them -- the exact root solver from
+    # EvaluateConfig.play_config (a fresh PlayConfig: use_solver_turn = 50) and the WLD solver inside simulations from the
+    # SELF-PLAY section, which ReversiPlayer reads through self.config.play (agent/player.py:237-238)
+    for variant, root_solver, sim_solver in (("default_solver", 50, 50), ("no_solver", 0, 0)):
+        cfg = Config()
+        pc = cfg.eval.play_config
+        pc.simulation_num_per_move, pc.parallel_search_num, pc.c_puct = 24, 1, 5
+        pc.use_solver_turn = root_solver
+        pc.use_solver_turn_in_simulation = 12345            # never read in an evaluation game
+        cfg.play.use_solver_turn_in_simulation = sim_solver
+        pc.resign_threshold = -0.35
+        pc.allowed_resign_turn = 12345                      # never read either: the resign rule uses config.play (agent/player.py:127)
+        cfg.play.allowed_resign_turn = 10
+        worker = ev.EvaluateWorker.__new__(ev.EvaluateWorker)
+        worker.config = cfg
+        games = []
+        try:
+            ev.ReversiPlayer = LoggingPlayer
+            for coin in (0.25, 0.75):               # random() < 0.5 -> the best model plays black (:70)
+                ev.random = lambda: coin
+                del log[:]
+                ng_win, best_is_black, score = worker.play_game(model(1.0), model(-1.0))
+                games.append(dict(best_is_black=bool(best_is_black), ng_win=ng_win, score=[int(score[0]), int(score[1])], plies=list(log)))
+        finally:
+            ev.ReversiPlayer, ev.random = real_player, real_random
+        out[variant] = dict(play=dict(simulation_num_per_move=24, parallel_search_num=1, c_puct=5, resign_threshold=-0.35, allowed_resign_turn=10,
+                                      thinking_loop=pc.thinking_loop, change_tau_turn=pc.change_tau_turn, noise_eps=pc.noise_eps,
+                                      use_solver_turn=root_solver, use_solver_turn_in_simulation=sim_solver), games=games)
+    return out
+
+
 def gen_ingest():
     """Trainer-side ingest: whole reference games -> the reference's own play_data file
     (lib/data_helper.py:23-25) -> its own loader + OptimizeWorker.convert_to_training_data (worker/optimize.py:215-231).
@@ -405,6 +462,11 @@ def main():
             json.dump(gen_mcts_features(), f)
         print("mcts feature golden vectors written")
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "eval":   # only (re)generate the evaluation-match fixture
+        with open(os.path.join(HERE, "eval_match.json"), "w") as f:
+            json.dump(gen_eval_match(), f)
+        print("evaluation match golden vectors written")
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "ingest":   # only (re)generate the trainer-ingest fixture
         np.savez_compressed(os.path.join(HERE, "ingest.npz"), **gen_ingest())
         print("ingest golden vectors written")
@@ -429,6 +491,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ingest.npz"), **gen_ingest())
     with open(os.path.join(HERE, "mcts_features.json"), "w") as f:
         json.dump(gen_mcts_features(), f)
+    with open(os.path.join(HERE, "eval_match.json"), "w") as f:
+        json.dump(gen_eval_match(), f)
     print("golden vectors written to", HERE)
 
 

@@ -304,3 +304,36 @@ def test_config_mirror_matches_reference_defaults_and_yaml():
             ref = ref_create(RefConfig, yaml.safe_load(f))
         mine = load_yaml(os.path.join(cfg_dir, name), project_dir="/tmp/rz_proj")
         compare(ref, mine, ("model", "play", "play_data"))
+
+
+def test_eval_play_config_matches_reference_effective_settings():
+    """What an evaluation game runs with: the reference's EvaluateConfig.play_config (a fresh PlayConfig + five overrides +
+    the YAML's eval.play_config), except the three fields ReversiPlayer reads from config.play even then
+    (agent/player.py:127,237-238,264) -- for the defaults and every config/*.yml of the reference."""
+    import oracle.ref_shims.install as shims
+    if not shims.available():
+        pytest.skip("reference sources not present")
+    shims.install()
+    import yaml
+    from moke_config import create_config as ref_create
+    from reversi_zero.config import Config as RefConfig
+    from reversi_zero_b200.config import load_yaml
+    cases = [(RefConfig(), Config(project_dir="/tmp/rz_proj"))]
+    for name in sorted(os.listdir("/root/reference/config")):
+        if name.endswith(".yml"):
+            with open(os.path.join("/root/reference/config", name), "rt") as f:
+                cases.append((ref_create(RefConfig, yaml.safe_load(f)), load_yaml(os.path.join("/root/reference/config", name), project_dir="/tmp/rz_proj")))
+    for ref, mine in cases:
+        want = dict(vars(ref.eval.play_config))
+        for k in ("allowed_resign_turn", "use_solver_turn_in_simulation", "virtual_loss"):
+            want[k] = getattr(ref.play, k)
+        got = vars(eval_play_config(mine))
+        for k, v in want.items():
+            if k == "share_mtcs_info_in_self_play":
+                continue                                   # evaluation players never share statistics (worker/evaluate.py:69-70)
+            gv = got[k]
+            norm = (lambda x: [list(y) for y in x]) if k == "schedule_of_simulation_num_per_move" else (lambda x: x)
+            assert norm(gv) == norm(v), (getattr(ref, "type", "?"), k)
+        # the reference's own Config object is accepted as well
+        got2 = vars(eval_play_config(ref))
+        assert all(got2[k] == want[k] for k in want if k not in ("share_mtcs_info_in_self_play",))

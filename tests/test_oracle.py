@@ -236,3 +236,37 @@ def _check_kept_table_games(ref, name):
         recs = [[[int(o), int(e)], [float(x) for x in p], int(z)] for (o, e), p, z in game.records()]
         assert hashlib.sha256(json.dumps(recs).encode()).hexdigest() == rg["records_sha256"], i
         assert game.n_expand == rg["expansions"] and game.black_z == rg["z"] and game.env.turn == rg["turn"], i
+
+
+def test_evaluation_match_exact_vs_reference(golden_dir):
+    """worker/evaluate.py:66-96 run UNMODIFIED with two deterministic evaluators (the challenger's value negated) behind
+    the reference's own ReversiModelAPI: every ply of the games -- position, move, root visit counts, solved plies, the
+    resignation -- and the verdict equal the oracle's two-network game (api / api_b / black_net), which the engine's
+    rz_engine_set_second_net path reproduces exactly on the GPU (tests/test_engine_gpu.py).  Variant "default_solver" is
+    what an evaluation game does when nobody touches the solver settings: exact root solver from the eval play_config,
+    WLD solver in simulations from the SELF-PLAY section (agent/player.py:100,237-238)."""
+    for variant, g in _load(golden_dir, "eval_match.json").items():
+        pl = g["play"]
+        pp = mcts.PlayParams(simulation_num_per_move=pl["simulation_num_per_move"], parallel_search_num=pl["parallel_search_num"], c_puct=pl["c_puct"],
+                             noise_eps=pl["noise_eps"], change_tau_turn=pl["change_tau_turn"], thinking_loop=pl["thinking_loop"],
+                             resign_threshold=pl["resign_threshold"], allowed_resign_turn=pl["allowed_resign_turn"], disable_resignation_rate=0,
+                             share_mtcs_info_in_self_play=False, use_solver_turn=pl["use_solver_turn"],
+                             use_solver_turn_in_simulation=pl["use_solver_turn_in_simulation"])
+        for i, ref in enumerate(g["games"]):
+            game = mcts.SelfPlayGame(pp, nn.FakeNetAPI(), seed=3, game_id=i, api_b=nn.FakeNetAPI(sign=-1.0),
+                                     black_net=0 if ref["best_is_black"] else 1)
+            assert game.enable_resign                                    # disable_resignation_rate = 0 (config.py:110)
+            game.play()
+            mine = sorted(game.plies + game.solved_plies, key=lambda r: r["turn"])
+            moves = [p for p in ref["plies"] if p["action"] >= 0]
+            assert len(mine) == len(moves), (variant, i)
+            for a, b in zip(mine, moves):
+                assert (a["own"], a["enemy"], a["action"]) == (b["own"], b["enemy"], b["action"]), (variant, i, a["turn"])
+                if "N" in a:
+                    assert list(a["N"]) == b["N"], (variant, i, a["turn"])
+            assert (game.actions[-1] is None) == (ref["plies"][-1]["action"] < 0), (variant, i)
+            e = game.env
+            assert [bin(e.black).count("1"), bin(e.white).count("1")] == ref["score"], (variant, i)
+            ng_is_black = not ref["best_is_black"]
+            ng_win = None if e.winner == 3 else int((e.winner == 1) == ng_is_black)
+            assert ng_win == ref["ng_win"], (variant, i)
