@@ -174,11 +174,15 @@ def test_search_with_real_network_matches_oracle():
     net.close()
 
 
-def test_evaluation_match_two_networks_exact():
+@pytest.mark.parametrize("kw", [dict(), dict(use_solver_turn=54, use_solver_turn_in_simulation=51, resign_threshold=-0.35, allowed_resign_turn=10,
+                                             disable_resignation_rate=0, noise_eps=0.0)])
+def test_evaluation_match_two_networks_exact(kw):
     """rz_engine_set_second_net (worker/evaluate.py:66-96): each search is evaluated by the mover's own network and the
     colours alternate with the game index.  Deterministic evaluators (the second one negates the value): whole games
-    must equal the oracle driven with the same two evaluators."""
-    pp = params(simulation_num_per_move=30, share_mtcs_info_in_self_play=False, change_tau_turn=0)
+    must equal the oracle driven with the same two evaluators (which equals the reference's EvaluateWorker.play_game,
+    tests/test_oracle.py::test_evaluation_match_exact_vs_reference) -- also with the solver and the resign rule on, as an
+    evaluation game has them by default."""
+    pp = params(simulation_num_per_move=30, share_mtcs_info_in_self_play=False, change_tau_turn=0, **kw)
     eng = make_engine(pp, games=3, seed=41, max_games=6)
     eng.set_second_net(None, enable=True)
     eng.run(finished_target=6)
@@ -189,9 +193,11 @@ def test_evaluation_match_two_networks_exact():
         replay_check(g)
         o = mcts.SelfPlayGame(pp, onn.FakeNetAPI(), seed=41, game_id=g["game_id"], api_b=onn.FakeNetAPI(sign=-1.0),
                               black_net=g["black_net"]).play()
-        assert [(p["own"], p["enemy"], p["action"], list(p["N"])) for p in g["plies"]] == \
-               [(p["own"], p["enemy"], p["action"], list(p["N"])) for p in o.plies]
-        assert g["winner"] == o.env.winner
+        theirs = sorted(o.plies + o.solved_plies, key=lambda r: r["turn"])
+        played = [p for p in g["plies"] if p["action"] >= 0]                 # a resignation is logged as a ply with action -1
+        assert [(p["own"], p["enemy"], p["action"], list(p["N"]) if p["recorded"] else None) for p in played] == \
+               [(p["own"], p["enemy"], p["action"], list(p["N"]) if "N" in p else None) for p in theirs]
+        assert g["winner"] == o.env.winner and (len(g["plies"]) > len(played)) == (o.actions[-1] is None)
     # the two evaluators really differ: the match is not symmetric
     assert len({(g["winner"], g["black_net"]) for g in games}) > 1 or len({g["black"] for g in games}) > 1
 
