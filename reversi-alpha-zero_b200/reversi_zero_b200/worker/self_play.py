@@ -294,8 +294,10 @@ class SelfPlayWorker:
                     self.buffer_games.append((_copy(g), [_copy(p) for p in gp]))
                 if pdc.enable_ggf_data:
                     self.ggf_lines.append(self._ggf_of(g, gp))
+                    if self.local_idx % pdc.nb_game_in_ggf_file == 0 or self.local_idx <= 5:   # worker/self_play.py:169-172
+                        self._flush_ggf()
                 if self.local_idx % pdc.nb_game_in_file == 0:
-                    self._flush_files()
+                    self._flush_files(ggf=False)
             with open(self.config.resource.self_play_game_idx_file, "wt") as f:
                 f.write(str(self.game_idx))
             new_sims = self.decide_simulation_num_per_move(self.game_idx)
@@ -332,7 +334,19 @@ class SelfPlayWorker:
             moves.append(f"{convert_action_to_move(int(p.action))}/{p.q * 10}/{p.n}")
         return make_ggf_string("RAZ", "RAZ", moves=moves)
 
-    def _flush_files(self, force=False):
+    def _flush_ggf(self):
+        """worker/self_play.py:196-207"""
+        if not self.ggf_lines:
+            return
+        rc = self.config.resource
+        game_id = datetime.now().strftime("%Y%m%d-%H%M%S.%f")
+        path = os.path.join(rc.self_play_ggf_data_dir, rc.ggf_filename_tmpl % game_id)
+        with open(path, "wt") as f:
+            for line in self.ggf_lines:
+                f.write(line + "\n")
+        self.ggf_lines = []
+
+    def _flush_files(self, force=False, ggf=True):
         rc, pdc = self.config.resource, self.config.play_data
         if self.buffer_games:
             n_plies = sum(len(pl) for _, pl in self.buffer_games)
@@ -357,13 +371,8 @@ class SelfPlayWorker:
             self.files_written.append(path)
             self.buffer_games = []
             self.remove_play_data()
-        if self.ggf_lines and (force or len(self.ggf_lines) >= pdc.nb_game_in_ggf_file):
-            game_id = datetime.now().strftime("%Y%m%d-%H%M%S.%f")
-            path = os.path.join(rc.self_play_ggf_data_dir, rc.ggf_filename_tmpl % game_id)
-            with open(path, "wt") as f:
-                for line in self.ggf_lines:
-                    f.write(line + "\n")
-            self.ggf_lines = []
+        if ggf and force:
+            self._flush_ggf()
 
     def remove_play_data(self):
         """worker/self_play.py:209-217"""

@@ -337,3 +337,45 @@ def test_eval_play_config_matches_reference_effective_settings():
         # the reference's own Config object is accepted as well
         got2 = vars(eval_play_config(ref))
         assert all(got2[k] == want[k] for k in want if k not in ("share_mtcs_info_in_self_play",))
+
+
+def test_harvest_file_rules_follow_reference(tmp_path, monkeypatch):
+    """SelfPlayWorker._harvest with a stand-in engine that hands over finished games: play_data files every
+    nb_game_in_file games (draws dropped with drop_draw_game_rate, worker/self_play.py:180-194), GGF files for each of the
+    first five games and then every nb_game_in_ggf_file games (:169-172,196-207), game-index file (:131-132)."""
+    import glob
+    import json
+    cfg, w = make_worker(tmp_path)
+    cfg.play_data.update(dict(nb_game_in_file=4, max_file_num=100, enable_ggf_data=True, nb_game_in_ggf_file=6, drop_draw_game_rate=0.5))
+    start = 0x0000000810000000, 0x0000001008000000
+
+    def finished(n, winners):
+        G = (_cabi.Game * n)()
+        P = (_cabi.Ply * n)()
+        for i in range(n):
+            G[i].game_id, G[i].first_ply, G[i].n_plies, G[i].winner = i, i, 1, winners[i]
+            G[i].black_z = {1: 1, 2: -1, 3: 0}[winners[i]]
+            P[i].own, P[i].enemy, P[i].player, P[i].recorded, P[i].action = start[0], start[1], 1, 1, 19
+            P[i].n_visit[19] = 7
+        return G, n, P, n
+
+    batches = [finished(13, [1, 2, 3, 3, 1, 1, 2, 3, 1, 2, 1, 1, 2])]
+
+    class Eng(FakeEngine):
+        def poll_raw(self):
+            return batches.pop(0) if batches else ((_cabi.Game * 1)(), 0, (_cabi.Ply * 1)(), 0)
+
+        def set_simulation_num(self, n):
+            pass
+    w.engine = Eng()
+    draws = iter([0.9, 0.1, 0.7])                    # drop_draw_game_rate <= random(): kept, dropped, kept
+    monkeypatch.setattr(np.random, "random", lambda: next(draws))
+    assert w._harvest() == 13
+    w._flush_files(force=True)
+    files = sorted(glob.glob(os.path.join(cfg.resource.play_data_dir, "play_*.json")))
+    # flush points after games 4, 8, 12 and the forced one at the end: 12 of the 13 games survive (one draw dropped)
+    per_file = [len(json.load(open(f))) // 8 for f in files]
+    assert per_file == [3, 4, 4, 1] and sum(per_file) == 12                                # the dropped draw was game 4
+    ggf = sorted(glob.glob(os.path.join(cfg.resource.self_play_ggf_data_dir, "*.ggf")))
+    assert [sum(1 for _ in open(f)) for f in ggf] == [1, 1, 1, 1, 1, 1, 6, 1]        # games 1-5 alone, 6, 7-12, then the forced rest
+    assert int(open(cfg.resource.self_play_game_idx_file).read()) == 13
