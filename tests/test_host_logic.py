@@ -379,3 +379,24 @@ def test_harvest_file_rules_follow_reference(tmp_path, monkeypatch):
     ggf = sorted(glob.glob(os.path.join(cfg.resource.self_play_ggf_data_dir, "*.ggf")))
     assert [sum(1 for _ in open(f)) for f in ggf] == [1, 1, 1, 1, 1, 1, 6, 1]        # games 1-5 alone, 6, 7-12, then the forced rest
     assert int(open(cfg.resource.self_play_game_idx_file).read()) == 13
+
+
+def test_player_mirror_takes_three_search_fields_from_the_self_play_section(tmp_path, monkeypatch):
+    """agent/player.py:127,237-238,264: with a separate play_config (evaluation, GUI) the reference still reads
+    allowed_resign_turn, use_solver_turn_in_simulation and virtual_loss from config.play; the mirror builds its engine
+    configuration accordingly (engine replaced by a stand-in: host logic only)."""
+    import reversi_zero_b200.agent.player as P
+    seen = {}
+
+    class StandIn:
+        def __init__(self, ecfg, model, device):
+            seen["cfg"] = ecfg
+    monkeypatch.setattr(P, "Engine", StandIn)
+    cfg = Config(project_dir=str(tmp_path))
+    cfg.play.use_solver_turn_in_simulation, cfg.play.virtual_loss = 48, 5
+    pc = eval_play_config(cfg)
+    pc.use_solver_turn_in_simulation, pc.virtual_loss = 0, 1
+    P.ReversiPlayer(cfg, None, play_config=pc)
+    assert (seen["cfg"].use_solver_turn_in_simulation, seen["cfg"].virtual_loss, seen["cfg"].simulation_num_per_move) == (48, 5, 400)
+    P.ReversiPlayer(cfg, None)
+    assert (seen["cfg"].use_solver_turn_in_simulation, seen["cfg"].virtual_loss, seen["cfg"].simulation_num_per_move) == (48, 5, 200)
