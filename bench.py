@@ -1,14 +1,20 @@
 #!/usr/bin/env python
 """bench.py -- self-play throughput of the B200 engine on BASELINE.json's primary configuration.
 
-A *step* is one engine wave over the resident games: the MCTS tick kernel (consume evaluations, expand,
-back up, decide moves, descend with virtual loss, gather leaves) followed by one launch of the fused
-tcgen05 policy/value tower over the gathered leaf batch.  Workload: ch5 network
-(256 filters x 10 residual blocks, random-init), 4096 concurrent games per GPU, simulation_num_per_move
-= 400, parallel_search_num = 8, c_puct = 5, virtual_loss = 3, noise_eps = 0.25, alpha = 0.5,
-change_tau_turn = 4, thinking_loop = 1, solver off, resignation off.  Games are started in steady state
-(engine warm_start: game phases spread uniformly) so that finished-games/second over a window of K waves is
-the steady-state rate; the plies-based estimate is printed beside it in `config`.
+A *step* is the waves of one whole search: simulation_num_per_move / parallel_search_num engine waves (50 at
+400 simulations), i.e. on average every resident game decides one move per step.  A wave is the MCTS tick
+kernel (consume evaluations, expand, back up, decide moves, descend with virtual loss, gather leaves)
+followed by one launch of the fused tcgen05 policy/value tower over the gathered leaf batch.  Workload
+(SURVEY 8(d) config 2): ch5 network (256 filters x 10 residual blocks, random-init), 4096 concurrent games
+per GPU, simulation_num_per_move = 400, parallel_search_num = 8, c_puct = 5, virtual_loss = 3, noise_eps =
+0.25, alpha = 0.5, change_tau_turn = 4, thinking_loop = 1, solver off, resignation off.
+
+`value` = games that FINISH inside the timed window / device time.  A game lasts ~3000 waves, longer than
+the window, so the resident games are started in the stationary state of a long run (engine warm_start +
+the measured waves-per-turn profile of complete games, profiles/full_games.json); the renewal estimate
+(node expansions/s / expansions per complete game) is printed beside it and must agree.  `e2e` = the same
+count through the public worker (host weights -> device, SelfPlayWorker.start() with its writer thread,
+play_*.json + GGF files on disk) over wall-clock time.
 
 Launch: python bench.py [--gpus N --steps K --warmup W] (N > 1 under torch.distributed.run, one rank per
 GPU).  `--impl reference` times the CPU port of the reference's own self-play worker (oracle/) on the host
@@ -84,6 +90,9 @@ def expansions_per_game():
     sims = PLAY_KW["simulation_num_per_move"]
     try:
         name = "full_games_solver_on.json" if PLAY_KW.get("use_solver_turn") else "full_games.json"
+        own = os.path.join(ROOT, "profiles", "full_games_sims%d.json" % sims)
+        if not PLAY_KW.get("use_solver_turn") and sims != 400 and os.path.exists(own):
+            name = os.path.basename(own)
         with open(os.path.join(ROOT, "profiles", name)) as f:
             d = json.load(f)
         if "sims=%d " % sims in d["workload"]:
@@ -91,6 +100,37 @@ def expansions_per_game():
         return float(d["expansions_per_game"]) * sims / 400.0, "ESTIMATE: profiles/%s (sims=400) scaled by sims/400" % name
     except Exception:
         return 21256.0 * sims / 400.0, "fallback: reference probe at sim=400 (SURVEY 3.1), scaled by sims/400"
+
+
+def waves_per_step():
+    """engine waves per bench step: the waves of one whole search (every game starts parallel_search_num simulations per wave)"""
+    return -(-PLAY_KW["simulation_num_per_move"] // PLAY_KW["parallel_search_num"])
+
+
+def warm_start_profile():
+    """weights[t] ~ engine waves a game spends at turn t, measured over complete games by `bench.py --full-games`
+    (profiles/full_games*.json: waves_by_turn).  The bench window is shorter than one game, so finished games per second
+    is only meaningful if the resident games start in the stationary state of a long run: turn t with probability
+    proportional to the time spent there (rz_engine_set_warm_start_profile).  Without a measured profile for this
+    simulation count the turns are equally likely and `value` is flagged."""
+    sims = PLAY_KW["simulation_num_per_move"]
+    name = "full_games_solver_on.json" if PLAY_KW.get("use_solver_turn") else ("full_games.json" if sims == 400 else "full_games_sims%d.json" % sims)
+    try:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            d = json.load(f)
+        w = [float(x) for x in d["waves_by_turn"]]
+        if len(w) == 60 and sum(w) > 0 and "sims=%d " % sims in d["workload"]:
+            return w, "stationary: turn drawn with profiles/%s waves_by_turn (%d complete games), first search a uniform fraction" % (name, d["games"])
+    except Exception:
+        pass
+    return None, "UNCALIBRATED: no waves_by_turn profile for this workload, turns 0..57 equally likely (finished-game count is biased)"
+
+
+def port_calibration():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "port_calibration_r02.json")))["summary"]
+    except Exception:
+        return None
 
 
 def cpu_baseline(budget_s, processes=None, torch_threads=1):
@@ -133,7 +173,8 @@ def workload_config(args, **extra):
                       "thinking_loop=1 solver=%s resign=off" % (args.games, args.sims, "on(50/50)" if PLAY_KW.get("use_solver_turn") else "off"),
              games_per_gpu=args.games, simulation_num_per_move=PLAY_KW["simulation_num_per_move"],
              l2="leaf batch + per-game trees (>20 GB) exceed L2; weights (23.7 MB fp16) are L2-resident by design",
-             step="one wave = MCTS tick kernel + tcgen05 tower launch over the leaf batch",
+             step="one step = simulation_num_per_move / parallel_search_num waves (every resident game decides about one move); "
+                  "one wave = MCTS tick kernel + tcgen05 tower launch over the leaf batch",
              arithmetic="network: f16 operands, f32 accumulate + f32 residual stream; MCTS: f32 W, f64 PUCT as numpy promotes; rules: u64", parallelism=f"dp{args.gpus} (games sharded by rank)")
     c.update(extra)
     return c
@@ -142,8 +183,9 @@ def workload_config(args, **extra):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=20, help="timed steps; one step = simulation_num_per_move / parallel_search_num waves")
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--no-writer-thread", action="store_true", help="e2e leg: harvest + write on the driving thread (A/B of the writer thread)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--games", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -198,11 +240,6 @@ def main():
     pp = SimpleNamespace(required_visit_to_decide_action=400, start_rethinking_turn=8, allowed_resign_turn=20,
                          disable_resignation_rate=0.1, **PLAY_KW)
 
-    def make_engine():
-        cfg = E.engine_cfg_from_play_config(pp, games=args.games, seed=20260922, eval_mode=E.EVAL_NET, first_game_id=rank,
-                                            game_id_stride=world, warm_start=True, overlap_groups=args.groups)
-        return E.Engine(cfg, net, local)
-
     if args.full_games:
         cfg = E.engine_cfg_from_play_config(pp, games=args.full_games, seed=20260922, eval_mode=E.EVAL_NET, max_games=args.full_games)
         eng = E.Engine(cfg, net, local)
@@ -211,28 +248,46 @@ def main():
         dt = time.perf_counter() - t0
         gs = eng.poll()
         st = eng.stats()
-        out = dict(games=len(gs), expansions_per_game=sum(g["expansions"] for g in gs) / len(gs),
+        by_turn = [0.0] * 60   # mean engine waves a game spends deciding the move at turn t (popcount - 4)
+        for g in gs:
+            for p in g["plies"]:
+                by_turn[min(59, bin(p["own"] | p["enemy"]).count("1") - 4)] += p["waves"] / len(gs)
+        out = dict(games=len(gs), waves_by_turn=by_turn, waves_per_game=sum(by_turn), expansions_per_game=sum(g["expansions"] for g in gs) / len(gs),
                    simulations_per_game=sum(g["simulations"] for g in gs) / len(gs), plies_per_game=sum(len(g["plies"]) for g in gs) / len(gs),
                    black_wins=sum(g["winner"] == 1 for g in gs), white_wins=sum(g["winner"] == 2 for g in gs), draws=sum(g["winner"] == 3 for g in gs),
                    seconds=dt, games_per_sec_cold_start=len(gs) / dt, waves=st["waves"], max_nodes_used=st["max_nodes_used"],
                    max_edges_used=st["max_edges_used"], workload=workload_config(args)["workload"],
                    recorded_plies_per_game=sum(sum(1 for p in g["plies"] if p["recorded"]) for g in gs) / len(gs))
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", "full_games_solver.json" if args.solver else "full_games.json"), "w") as f:
+        name = "full_games_solver_on.json" if args.solver else ("full_games.json" if args.sims == 400 else "full_games_sims%d.json" % args.sims)
+        with open(os.path.join(ROOT, "gpurun_out", name), "w") as f:
             json.dump(out, f)
         _emit(json.dumps(out))
         return
 
     # ---- device-resident measurement: `value` -------------------------------------------------------------
-    eng = make_engine()
-    eng.run(max_waves=args.warmup)
+    # one step = the waves of one whole search (simulation_num_per_move / parallel_search_num): on average every resident
+    # game decides one move per step, so a window of K steps sees K/60 of the resident games finish
+    wps = waves_per_step()
+    profile, profile_src = warm_start_profile()
+
+    def make_engine(groups, seed):
+        cfg = E.engine_cfg_from_play_config(pp, games=args.games, seed=seed, eval_mode=E.EVAL_NET, first_game_id=rank,
+                                            game_id_stride=world, warm_start=True, overlap_groups=groups)
+        eng = E.Engine(cfg, net, local)
+        if profile is not None:
+            eng.set_warm_start_profile(profile)
+        return eng
+
+    eng = make_engine(args.groups, 20260922)
+    eng.run(max_waves=args.warmup * wps)
     s0 = eng.stats()
     sampler = ClockSampler(local)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     sampler.start()
-    eng.run(max_waves=args.steps)
+    eng.run(max_waves=args.steps * wps)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -244,12 +299,10 @@ def main():
     eng.close()
     # roofline leg: the same workload with ONE slot group, so that the CUDA events around each tower launch bracket
     # exactly that kernel (with two groups a launch's events also contain the wait for the other group's launch)
-    cfg1 = E.engine_cfg_from_play_config(pp, games=args.games, seed=20260922, eval_mode=E.EVAL_NET, first_game_id=rank,
-                                         game_id_stride=world, warm_start=True, overlap_groups=1)
-    eng1 = E.Engine(cfg1, net, local)
-    eng1.run(max_waves=args.warmup)
+    eng1 = make_engine(1, 20260922)
+    eng1.run(max_waves=max(3, args.warmup) * 4)
     r0 = eng1.stats()
-    eng1.run(max_waves=max(24, args.steps // 5))
+    eng1.run(max_waves=48)
     r1 = eng1.stats()
     eng1.close()
     roof = {k: r1[k] - r0[k] for k in r1}
@@ -264,13 +317,13 @@ def main():
     secs = run_ms / 1e3
     exp_per_s = exps / secs
     epg, epg_src = expansions_per_game()
-    # steady-state rate of complete games: the network evaluations are ~all of the cost, the leaf batches stay full
-    # whatever the mix of game phases, so games/s = expansions/s / (expansions per complete game).  The raw count of
-    # games that happened to finish inside the window is reported next to it (it over-counts: endgame plies are cheap,
-    # so warm-started slots near the end of their game finish in a burst).
-    value = exp_per_s / epg
+    # `value`: games that FINISHED inside the timed window / device time of the window (the slots start in the stationary
+    # state of a long run, see warm_start_profile).  Printed beside it: the renewal estimate expansions/s / (expansions per
+    # complete game) -- the same rate with less counting noise; the two must agree.
+    value = games / secs
+    value_est = exp_per_s / epg
 
-    # ---- end to end through the public worker path: host weights -> device, waves, harvest, play_data files ----
+    # ---- end to end through the public worker path: host weights -> device, waves, harvest thread, play_data files ----
     import tempfile
     from reversi_zero_b200.config import Config
     from reversi_zero_b200.worker.self_play import SelfPlayWorker
@@ -281,9 +334,12 @@ def main():
     cfg.play.schedule_of_simulation_num_per_move = [(0, PLAY_KW["simulation_num_per_move"])]
     cfg.play.use_solver_turn = PLAY_KW.get("use_solver_turn", 0)
     cfg.play.use_solver_turn_in_simulation = PLAY_KW.get("use_solver_turn_in_simulation", 0)
-    cfg.play_data.nb_game_in_file = 64
-    cfg.play_data.enable_ggf_data = False
+    # output settings of config/ch5.yml:3-7: one game per play_data file, at most 800 files kept, half of the draws dropped;
+    # GGF records on (config.py:123-124)
+    cfg.play_data.update(dict(nb_game_in_file=1, max_file_num=800, drop_draw_game_rate=0.5, enable_ggf_data=True, nb_game_in_ggf_file=100))
     cfg.b200.games_per_gpu = args.games
+    cfg.b200.seed = 20260923
+    cfg.b200.warm_start, cfg.b200.warm_start_profile = True, profile
     cfg.resource.create_directories()
     torch.cuda.synchronize()
     if world > 1:
@@ -295,29 +351,26 @@ def main():
     elif world > 1:
         net2.load_blob_dev(t_blob)
     worker = SelfPlayWorker(cfg, net=net2, device=local, rank=rank, world_size=world)
-    ecfg = E.engine_cfg_from_play_config(pp, games=args.games, seed=20260923, eval_mode=E.EVAL_NET, first_game_id=rank,
-                                         game_id_stride=world, warm_start=True)
-    worker.engine = E.Engine(ecfg, net2, local)
-    worker.engine.run(max_waves=args.steps)
-    n_e2e = worker._harvest()
-    worker._flush_files(force=True)
+    n_e2e = worker.start(max_waves=args.steps * wps, threaded=not args.no_writer_thread)   # engine creation, waves, harvest, files
     torch.cuda.synchronize()
     e2e_secs = time.perf_counter() - t0
-    e2e_exps = float(worker.engine.stats()["expansions"])
-    file_bytes = sum(os.path.getsize(p) for p in worker.files_written)
-    d2h = n_e2e * (48 + 60 * 288) + (args.steps // 8 + 1) * (80 + 2 * args.games)
-    e2e_t = torch.tensor([float(n_e2e), e2e_secs, e2e_exps], dtype=torch.float64, device=f"cuda:{local}")
+    st_e2e = worker.engine.stats()
+    e2e_exps = float(st_e2e["expansions"])
+    file_bytes = worker.bytes_written
+    n_files = len(worker.files_written)
+    d2h = n_e2e * (56 + 60 * 288) + (args.steps * wps // 8 + 1) * (80 + 2 * args.games)
+    e2e_t = torch.tensor([float(n_e2e), e2e_secs, e2e_exps, float(file_bytes), float(n_files), float(d2h)], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         g_ = e2e_t.clone(); dist.all_reduce(g_, op=dist.ReduceOp.SUM)
         m_ = e2e_t.clone(); dist.all_reduce(m_, op=dist.ReduceOp.MAX)
-        n_e2e_all, e2e_secs, e2e_exps = float(g_[0]), float(m_[1]), float(g_[2])
+        n_e2e_all, e2e_secs, e2e_exps, file_bytes, n_files, d2h = float(g_[0]), float(m_[1]), float(g_[2]), float(g_[3]), float(g_[4]), float(g_[5])
     else:
         n_e2e_all = float(n_e2e)
-    e2e_value = e2e_exps / e2e_secs / expansions_per_game()[0]
+    e2e_value = n_e2e_all / e2e_secs
+    e2e_value_est = e2e_exps / e2e_secs / epg
     worker.engine.close()
     import shutil
     shutil.rmtree(tmp, ignore_errors=True)
-    st_e2e = None
 
     if rank != 0:
         if world > 1:
@@ -335,7 +388,8 @@ def main():
     except Exception:
         pass
     roofline = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic,
-                    peak_source=f"{pk_src} bf16_tflops_sustained", kernel="net_tower_kernel",
+                    peak_source=f"{pk_src} bf16_tflops_sustained", frac_of_burst_peak=achieved / pk.get("bf16_tflops", peak),
+                    kernel="net_tower_kernel",
                     launches=nn_launches, avg_launch_ms=roof["nn_ms"] / max(1, nn_launches),
                     mean_leaf_batch=rank_exps / max(1, nn_launches), share_of_step=roof["nn_ms"] / max(1e-9, roof["run_ms"]),
                     mcts_tick_share_of_step=roof["mcts_ms"] / max(1e-9, roof["run_ms"]),
@@ -345,22 +399,32 @@ def main():
     if not args.no_cpu_baseline:
         r, gps = cpu_baseline(budget_s=15.0)
         cb = dict(value=gps, unit="games/s", cores=r["processes"], kind="port",
-                  sample=f"{r['processes']} processes x 15 s of one game each from the opening (400 sims/move); {r['expansions']} expansions; "
+                  sample=f"{r['processes']} processes x 15 s of one game each from the opening ({args.sims} sims/move); {r['expansions']} expansions; "
                          f"games/s = expansions/s / {epg:.0f}",
-                  expansions_per_sec=r["expansions_per_s"], mean_nn_batch=r["mean_batch"])
+                  expansions_per_sec=r["expansions_per_s"], mean_nn_batch=r["mean_batch"],
+                  value_per_core=gps / max(1, r["processes"]),
+                  host_cores_equal_to_this_run=(e2e_value / (gps / max(1, r["processes"]))) if gps > 0 else None,
+                  port_vs_unmodified_reference=port_calibration())
 
     line = dict(metric="self_play_games_per_sec", value=value, unit="games/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=run_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16",
                 data="synthetic (random-init ch5 weights, self-generated games)",
-                config=workload_config(args, games_finished_in_window=games, games_per_sec_finished_in_window=games / secs,
-                                       plies_decided=plies, expansions_per_game=epg, expansions_per_game_source=epg_src,
-                                       value_definition="node_expansions_per_sec / expansions_per_game",
+                config=workload_config(args, waves_per_step=wps, games_finished_in_window=games,
+                                       value_definition="games finished inside the timed window / device time of the window",
+                                       value_renewal_estimate=value_est, measured_over_estimate=value / value_est if value_est else None,
+                                       plies_decided=plies, plies_per_sec_over_60=plies / secs / PLIES_PER_GAME,
+                                       expansions_per_game=epg, expansions_per_game_source=epg_src,
+                                       warm_start=profile_src,
                                        timing="CUDA events on the engine streams, first to last wave; max over ranks"),
                 node_expansions_per_sec=exp_per_s, simulations_per_sec=sims / secs,
                 roofline=roofline, cpu_baseline=cb, clocks=clocks,
                 e2e=dict(value=e2e_value, unit="games/s", h2d_bytes_per_step=int(n_blob * 4 / args.steps), d2h_bytes_per_step=int(d2h / args.steps),
-                         play_data_bytes_written=file_bytes, games_harvested=n_e2e_all, expansions=e2e_exps, seconds=e2e_secs,
-                         what="host weight blob -> device + pack, engine create, K waves, harvest, play_*.json written"),
+                         play_data_bytes_written=int(file_bytes), play_data_files_written=int(n_files), games_harvested=n_e2e_all,
+                         value_renewal_estimate=e2e_value_est, expansions=e2e_exps, seconds=e2e_secs,
+                         writer_thread=not args.no_writer_thread,
+                         what="wall clock of: host weight blob -> device + pack, engine creation, K steps of waves driven by "
+                              "SelfPlayWorker.start() while its writer thread harvests finished games (D2H) and writes one "
+                              "play_*.json per game + GGF records (ch5.yml output settings); value = games written / wall seconds"),
                 gpu_launches=int(launches))
     _emit(json.dumps(line))
     if world > 1:

@@ -17,7 +17,7 @@
  *   - board encoding (lib/bitboard.py:11-17): uint64 bitboard, bit i = square y*8+x, bit 0 top-left.
  *   - Player: 1 = black, 2 = white (env/reversi_env.py:9); Winner: 0 = none, 1 = black, 2 = white,
  *     3 = draw (env/reversi_env.py:11).
- *   - handles are not thread-safe; one engine per GPU driven by one host thread.
+ *   - handles are not thread-safe; one engine per GPU driven by one host thread (exception: rz_engine_poll, see there).
  */
 #ifndef RZ_ENGINE_H
 #define RZ_ENGINE_H
@@ -37,7 +37,7 @@ extern "C" {
 #define RZ_ECAPACITY (-5) /* an engine arena overflowed (nodes / edges / records) */
 #define RZ_EIO (-6)      /* file I/O failed */
 
-#define RZ_ABI_VERSION 1
+#define RZ_ABI_VERSION 2
 
 int rz_abi_version(void);
 const char* rz_last_error(void);
@@ -180,6 +180,9 @@ typedef struct rz_engine_cfg {
     int32_t max_searches_per_game;  /* sizes the per-game node arena: nodes = this x simulation_num_per_move;
                                        0 = 60 x min(thinking_loop, 2).  Rethinking (thinking_loop > 1) is skipped
                                        when the arena could no longer hold one search per remaining ply. */
+    int32_t arena_simulation_num;   /* the largest simulation count rz_engine_set_simulation_num will be asked for during this
+                                       engine's life (the maximum over schedule_of_simulation_num_per_move and .force-sim,
+                                       worker/self_play.py:262-272); the arenas are sized for it.  0 = simulation_num_per_move. */
     float c_puct;                   /* :135 */
     float noise_eps;                /* :136 */
     float dirichlet_alpha;          /* :137 */
@@ -200,7 +203,8 @@ typedef struct rz_ply {
     uint8_t player;       /* 1 black / 2 white */
     uint8_t loops;        /* thinking loops used */
     uint8_t recorded;     /* 1 if this ply is training data (0 for a resignation) */
-    uint8_t pad[3];
+    uint8_t pad;
+    uint16_t waves;       /* engine waves this slot spent deciding the ply (saturating; measurement only, no reference twin) */
     float n;              /* ActionWithEvaluation.n */
     float q;              /* ActionWithEvaluation.q */
 } rz_ply;
@@ -219,6 +223,9 @@ typedef struct rz_game {
     uint8_t turn;           /* ReversiEnv.turn at the end */
     uint8_t black_net;      /* evaluation matches: 0 = black was played by the first network, 1 = by the second */
     uint8_t pad[2];
+    int32_t table_nodes;    /* positions in the slot's statistics table at the end of the game (half of the reference's
+                               len(mtcs_info.var_p), which also holds every colour-swapped mirror key, worker/self_play.py:127) */
+    int32_t pad2;
 } rz_game;
 
 typedef struct rz_stats {
@@ -237,12 +244,24 @@ int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net /* may be NULL for RZ
                      rz_engine** out);
 int rz_engine_destroy(rz_engine* e);
 /* run waves until at least `finished_target` games (cumulative) have finished or `max_waves` waves
- * were executed (0 = no limit).  Finished games accumulate in a host-side queue until polled. */
+ * were executed (0 = no limit).  Finished games accumulate in a host-side queue until polled.
+ * rz_engine_poll (and only it) may be called from a second host thread while rz_engine_run is in progress: the queue is
+ * a mutex-protected single-producer / single-consumer hand-off, which is how the worker's writer thread overlaps
+ * harvesting and play_data output with the waves (the reference overlaps through processes, worker/self_play.py:36-41). */
 int rz_engine_run(rz_engine* e, uint64_t finished_target, uint64_t max_waves);
 /* pop up to game_cap finished games (and their plies, up to ply_cap) from the queue. */
 int rz_engine_poll(rz_engine* e, rz_game* games, size_t game_cap, size_t* n_games, rz_ply* plies, size_t ply_cap,
                    size_t* n_plies);
 int rz_engine_stats(rz_engine* e, rz_stats* out);
+/* no slot starts a game whose local index (slot + games already started by the slot x games) is >= max_games; 0 = no
+ * limit, 1 = let the resident games finish and start nothing (rz_engine_run then returns when every slot is idle). */
+int rz_engine_set_max_games(rz_engine* e, uint64_t max_games);
+/* warm_start only: weight[t] (t = 0 .. n-1, n <= 60) is proportional to the time a game spends at turn t; the first
+ * game of every slot then begins at turn t with probability weight[t] / sum and its first search runs a uniformly drawn
+ * fraction of simulation_num_per_move, i.e. the slots start in the stationary state of an engine that has been running
+ * for a long time (used by bench.py, which measures finished games per second over a window shorter than a game).
+ * Without this call the turns 0..57 are equally likely.  Call before the first rz_engine_run. */
+int rz_engine_set_warm_start_profile(rz_engine* e, const float* weight, int n);
 /* change the per-move simulation count for games started from now on
  * (SelfPlayWorker.decide_simulation_num_per_move, worker/self_play.py:262-272). */
 int rz_engine_set_simulation_num(rz_engine* e, int32_t sims);

@@ -414,7 +414,8 @@ struct WCtx {
             pl.n_visit[sq] = ((nd.legal >> sq) & 1ULL) ? ed[popc64(nd.legal & ((1ULL << sq) - 1))].n : 0;
         if (lane == 0) {
             pl.own = own; pl.enemy = enemy;
-            pl.player = (uint8_t)pid; pl.loops = 0; pl.pad[0] = pl.pad[1] = pl.pad[2] = 0;
+            pl.player = (uint8_t)pid; pl.loops = 0; pl.pad = 0;
+            pl.waves = (uint16_t)(sl.ply_waves > 0xFFFFu ? 0xFFFFu : sl.ply_waves);
             pl.n = 999.f; pl.q = sgn;
             pl.action = (int16_t)mv;
             pl.recorded = 0;  // "not save move as play data", player.py:102
@@ -422,6 +423,7 @@ struct WCtx {
         }
         __syncwarp();
         sl.ply++;
+        sl.ply_waves = 0;
         env_step(sl.env, mv);
         if (sl.env.done) { finish_game(); return; }
         const bool b2 = sl.env.next_player == 1;
@@ -455,14 +457,19 @@ struct WCtx {
         }
         sl.n_expand = 0; sl.n_rootsel = 0; sl.n_sims = 0; sl.ply = 0; sl.tl = 0;
         sl.n_searched_plies = 0; sl.n_solves = 0; sl.root_req = 0;
-        sl.resigned_mask = 0; sl.search_only = 0;
+        sl.resigned_mask = 0; sl.search_only = 0; sl.ply_waves = 0;
         for (int k = 0; k < c.K; ++k) dstat[k] = D_FREE;
         sl.enable_resign = (uint8_t)((double)c.disable_resignation_rate <= u01(draw(c.seed, sl.game_id, 0, P_GAME, 0).x));
         if (lane == 0) atomicAdd(&p.status->games_started, 1ULL);
         sl.phase = PH_DECIDE;
         if (c.warm_start && sl.games_played == 1) {
+            // the slot's first game starts at turn `pre` (drawn from the profile, rz_engine_set_warm_start_profile) after
+            // `pre` random legal plies, and its first search is a uniformly drawn part of a whole one: the state of a slot
+            // met at a random moment of a long run.  Pre-played plies are neither searched nor recorded.
             const U4 r0 = draw(c.seed, sl.game_id, 1, P_GAME, 0);
-            const int pre = (int)(u01(r0.x) * 58.0);
+            const float u = (float)u01(r0.x);
+            int pre = 0;
+            while (pre < 59 && u >= c.warm_cdf[pre]) ++pre;
             for (int i = 0; i < pre && !sl.env.done; ++i) {
                 const bool b = sl.env.next_player == 1;
                 const u64 legal = find_correct_moves(b ? sl.env.black : sl.env.white, b ? sl.env.white : sl.env.black);
@@ -473,6 +480,10 @@ struct WCtx {
             else if (sl.env.turn > 0) {
                 const bool b = sl.env.next_player == 1;
                 begin_ply(b ? sl.env.black : sl.env.white, b ? sl.env.white : sl.env.black, sl.env.next_player);
+                if (sl.phase == PH_SEARCH) {
+                    const uint32_t part = (uint32_t)(u01(r0.y) * (double)c.S) + 1u;
+                    sl.sims_target = part < (uint32_t)c.S ? part : (uint32_t)c.S;
+                }
             }
         }
     }
@@ -485,6 +496,7 @@ struct WCtx {
             g.winner = sl.env.winner; g.black_z = sl.env.winner == 1 ? 1 : (sl.env.winner == 2 ? -1 : 0);
             g.resign_enabled = sl.enable_resign; g.resigned_mask = sl.resigned_mask; g.turn = sl.env.turn;
             g.black_net = sl.black_net; g.pad[0] = g.pad[1] = 0;
+            g.table_nodes = (int32_t)sl.n_nodes; g.pad2 = 0;
             atomicMax(&p.status->max_nodes, (unsigned long long)sl.n_nodes);
             atomicMax(&p.status->max_edges, (unsigned long long)sl.n_edges);
             __threadfence();
@@ -569,7 +581,8 @@ struct WCtx {
             pl.n_visit[sq] = ((nd.legal >> sq) & 1ULL) ? ed[popc64(nd.legal & ((1ULL << sq) - 1))].n : 0;
         if (lane == 0) {
             pl.own = own; pl.enemy = enemy;
-            pl.player = (uint8_t)pid; pl.loops = sl.tl; pl.pad[0] = pl.pad[1] = pl.pad[2] = 0;
+            pl.player = (uint8_t)pid; pl.loops = sl.tl; pl.pad = 0;
+            pl.waves = (uint16_t)(sl.ply_waves > 0xFFFFu ? 0xFFFFu : sl.ply_waves);
             pl.n = (float)ed[choice].n; pl.q = (float)q_choice;
             pl.action = resign ? (int16_t)-1 : (int16_t)action;
             pl.recorded = resign ? 0 : 1;
@@ -577,6 +590,7 @@ struct WCtx {
         }
         __syncwarp();
         sl.ply++;
+        sl.ply_waves = 0;
         sl.n_searched_plies++;
         sl.tl = 0;
         env_step(sl.env, resign ? -1 : action);
@@ -597,6 +611,7 @@ __global__ void __launch_bounds__(kWarpTickThreads) tick_warp_kernel(const DevCf
     WCtx x(c, p, s, lane);
     Slot& sl = x.sl;
     if (sl.phase == PH_IDLE) return;
+    if (sl.phase == PH_SEARCH || sl.phase == PH_SOLVE) sl.ply_waves++;
     if (sl.phase == PH_SEARCH) {  // 1. consume the previous wave's evaluations in request order
         // ... once every endgame solve the slot asked for is finished: a solve may take several waves, and until then the
         // slot does nothing (the search result cannot depend on how long a solve took).  Network results that arrived in

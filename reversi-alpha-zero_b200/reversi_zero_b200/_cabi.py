@@ -32,14 +32,14 @@ class EngineCfg(C.Structure):
         "games", "simulation_num_per_move", "parallel_search_num", "virtual_loss", "change_tau_turn", "thinking_loop",
         "required_visit_to_decide_action", "start_rethinking_turn", "allowed_resign_turn", "use_resign_threshold",
         "share_mtcs_info", "eval_mode", "net_impl", "max_plies", "warm_start", "overlap_groups", "max_sims_per_wave", "use_solver_turn", "use_solver_turn_in_simulation",
-        "reset_mtcs_info_per_game", "max_searches_per_game")] + [(n, C.c_float) for n in (
+        "reset_mtcs_info_per_game", "max_searches_per_game", "arena_simulation_num")] + [(n, C.c_float) for n in (
             "c_puct", "noise_eps", "dirichlet_alpha", "resign_threshold", "disable_resignation_rate")] + [
         (n, C.c_uint64) for n in ("seed", "first_game_id", "game_id_stride", "max_games")]
 
 
 class Ply(C.Structure):
     _fields_ = [("own", C.c_uint64), ("enemy", C.c_uint64), ("n_visit", C.c_int32 * 64), ("action", C.c_int16),
-                ("player", C.c_uint8), ("loops", C.c_uint8), ("recorded", C.c_uint8), ("pad", C.c_uint8 * 3),
+                ("player", C.c_uint8), ("loops", C.c_uint8), ("recorded", C.c_uint8), ("pad", C.c_uint8), ("waves", C.c_uint16),
                 ("n", C.c_float), ("q", C.c_float)]
 
 
@@ -47,7 +47,7 @@ class Game(C.Structure):
     _fields_ = [("game_id", C.c_uint64), ("black", C.c_uint64), ("white", C.c_uint64), ("first_ply", C.c_int32),
                 ("n_plies", C.c_int32), ("expansions", C.c_int32), ("simulations", C.c_int32), ("winner", C.c_uint8),
                 ("black_z", C.c_int8), ("resign_enabled", C.c_uint8), ("resigned_mask", C.c_uint8), ("turn", C.c_uint8),
-                ("black_net", C.c_uint8), ("pad", C.c_uint8 * 2)]
+                ("black_net", C.c_uint8), ("pad", C.c_uint8 * 2), ("table_nodes", C.c_int32), ("pad2", C.c_int32)]
 
 
 class PlayRow(C.Structure):
@@ -94,6 +94,8 @@ SIGNATURES = {
     "rz_engine_poll": (C.c_int, [vp, C.POINTER(Game), sz, C.POINTER(sz), C.POINTER(Ply), sz, C.POINTER(sz)]),
     "rz_engine_stats": (C.c_int, [vp, C.POINTER(Stats)]),
     "rz_engine_set_simulation_num": (C.c_int, [vp, C.c_int32]),
+    "rz_engine_set_warm_start_profile": (C.c_int, [vp, f32p, C.c_int]),
+    "rz_engine_set_max_games": (C.c_int, [vp, C.c_uint64]),
     "rz_engine_set_second_net": (C.c_int, [vp, vp, C.c_int]),
     "rz_engine_set_resign_threshold": (C.c_int, [vp, C.c_int, C.c_float]),
     "rz_engine_search_root": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, i32p, f32p]),

@@ -99,6 +99,8 @@ class B200Config(_Section):
         self.net_impl = 0           # RZ_NET_IMPL_AUTO
         self.weight_seed = 0        # random-init seed used when no weights exist (`--new`, agent/api.py:112-114)
         self.tensorboard = False    # write self/time, self/turn scalars like worker/self_play.py:125-129
+        self.warm_start = False     # benchmark only: the first game of every slot starts mid-game (rz_engine_cfg.warm_start)
+        self.warm_start_profile = None  # ... at a turn drawn with these weights (rz_engine_set_warm_start_profile)
         self.write_play_rows = False  # also write play_*.rzrows (280 B per ply) for the device-side ingest, worker/ingest.py
 
 

@@ -11,7 +11,7 @@ EVAL_NET, EVAL_FAKE = 0, 1
 
 def engine_cfg_from_play_config(pc, pdc=None, games=1024, seed=0, eval_mode=EVAL_NET, net_impl=0, first_game_id=0,
                                 game_id_stride=1, max_games=0, warm_start=False, overlap_groups=0,
-                                max_searches_per_game=0, use_solver=True):
+                                max_searches_per_game=0, use_solver=True, arena_simulation_num=0):
     """Build an rz_engine_cfg from objects with the reference's PlayConfig / PlayDataConfig fields
     (config.py:116-166)."""
     cfg = _cabi.EngineCfg()
@@ -32,6 +32,7 @@ def engine_cfg_from_play_config(pc, pdc=None, games=1024, seed=0, eval_mode=EVAL
     cfg.warm_start = 1 if warm_start else 0
     cfg.overlap_groups = overlap_groups
     cfg.max_searches_per_game = max_searches_per_game
+    cfg.arena_simulation_num = int(arena_simulation_num or 0)
     cfg.max_sims_per_wave = int(getattr(pc, "max_sims_per_wave", 0) or 0)
     cfg.reset_mtcs_info_per_game = int(getattr(pc, "reset_mtcs_info_per_game", 1) or 1) if cfg.share_mtcs_info else 1
     cfg.use_solver_turn = int(getattr(pc, "use_solver_turn", 0) or 0) if use_solver else 0
@@ -81,11 +82,12 @@ class Engine:
                 for j in range(g.first_ply, g.first_ply + g.n_plies):
                     p = plies[j]
                     pl.append(dict(own=int(p.own), enemy=int(p.enemy), N=np.array(p.n_visit[:], dtype=np.int64), action=int(p.action),
-                                   pid=int(p.player), loops=int(p.loops), recorded=bool(p.recorded), n=float(p.n), q=float(p.q)))
+                                   pid=int(p.player), loops=int(p.loops), recorded=bool(p.recorded), n=float(p.n), q=float(p.q),
+                                   waves=int(p.waves)))
                 out.append(dict(game_id=int(g.game_id), black=int(g.black), white=int(g.white), winner=int(g.winner),
                                 black_z=int(g.black_z), expansions=int(g.expansions), simulations=int(g.simulations),
                                 resign_enabled=bool(g.resign_enabled), resigned_mask=int(g.resigned_mask), turn=int(g.turn),
-                                black_net=int(g.black_net), plies=pl))
+                                black_net=int(g.black_net), table_nodes=int(g.table_nodes), plies=pl))
         return out
 
     def stats(self):
@@ -95,6 +97,15 @@ class Engine:
 
     def set_simulation_num(self, sims):
         _cabi.check(_cabi.lib().rz_engine_set_simulation_num(self._h, int(sims)), "rz_engine_set_simulation_num")
+
+    def set_max_games(self, n):
+        """no slot starts a game whose local index is >= n (0 = unlimited); 1 drains the engine"""
+        _cabi.check(_cabi.lib().rz_engine_set_max_games(self._h, int(n)), "rz_engine_set_max_games")
+
+    def set_warm_start_profile(self, weights):
+        w = np.ascontiguousarray(weights, dtype=np.float32)
+        _cabi.check(_cabi.lib().rz_engine_set_warm_start_profile(self._h, w.ctypes.data_as(_cabi.f32p), int(w.size)),
+                    "rz_engine_set_warm_start_profile")
 
     def set_second_net(self, net_b=None, enable=True):
         """evaluation matches: even local game indices -> first network plays black, odd -> second network."""

@@ -101,6 +101,21 @@ def calc_flip_batch(pos, own, enemy):
     return out
 
 
+def dihedral_batch(x, t, device="cuda:0"):
+    """rz_dihedral_dev over arrays: out[i] = flip_vertical if t[i] & 4, then (t[i] & 3) x rotate90 of x[i]
+    (lib/bitboard.py:119-159 in the order of agent/player.py:166-179,300-305) -- the device code the engine's leaf
+    gather and the ingest kernel use.  Device buffers through torch (plumbing); host arrays in / out."""
+    import torch
+    from .. import device as D
+    x = _u64(x)
+    t = np.ascontiguousarray(np.broadcast_to(np.asarray(t, dtype=np.uint8), x.shape))
+    dx, dt = D.to_device(x, device), D.to_device(t, device)
+    out = D.empty(x.size, np.uint64, device)
+    _cabi.check(_cabi.lib().rz_dihedral_dev(D.ptr(dx), D.ptr(dt), D.ptr(out), x.size, D.stream_ptr()), "rz_dihedral_dev")
+    torch.cuda.synchronize()
+    return D.to_numpy_u64(out)
+
+
 def step_batch(black, white, next_player, turn, done, winner, action, want_legal=False):
     """In place on contiguous uint64 / uint8 arrays; action int8 with -1 = resign.  Returns legal masks or None."""
     n = black.size

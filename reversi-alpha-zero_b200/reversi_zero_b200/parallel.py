@@ -26,6 +26,11 @@ def broadcast_blob(model_config, blob_or_none, device):
     return t
 
 
+def control_device(cuda_index):
+    """device of the small control tensors: the GPU under NCCL, the host under gloo (CPU tests)"""
+    return f"cuda:{cuda_index}" if dist.get_backend() == "nccl" else "cpu"
+
+
 def sum_over_ranks(values, device):
     t = torch.tensor(values, dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)

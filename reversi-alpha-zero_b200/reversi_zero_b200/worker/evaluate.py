@@ -66,15 +66,17 @@ def _eval_field(config, name, default):
     return getattr(ev, name, default) if ev is not None else default
 
 
-def play_match(config, best_net, ng_net, game_num, device=0, seed=0):
-    """-> (results, games): results[i] = 1 challenger won, 0 lost, None draw (worker/evaluate.py:84-96)."""
+def play_match(config, best_net, ng_net, game_num, device=0, seed=0, first_game_id=0):
+    """-> (results, games): results[i] = 1 challenger won, 0 lost, None draw (worker/evaluate.py:84-96).
+    ``seed`` / ``first_game_id`` select the Philox streams (dihedral choices, move sampling) of the match: callers give
+    every match its own, so that the randomness of consecutive matches is independent like the reference's."""
     pc = eval_play_config(config)
     slots = min(game_num, getattr(getattr(config, "b200", None), "games_per_gpu", 4096))
-    cfg = engine_cfg_from_play_config(pc, games=slots, seed=seed, eval_mode=EVAL_NET, max_games=game_num)
+    cfg = engine_cfg_from_play_config(pc, games=slots, seed=seed, eval_mode=EVAL_NET, max_games=game_num, first_game_id=first_game_id)
     eng = Engine(cfg, best_net, device)
     eng.set_second_net(ng_net)
     eng.run(finished_target=game_num)
-    games = sorted(eng.poll(), key=lambda g: g["game_id"])
+    games = sorted(eng.poll(), key=lambda g: g["game_id"])   # game-id order == local game index order (colours alternate with it)
     eng.close()
     results = []
     for g in games:
@@ -111,6 +113,7 @@ class EvaluateWorker:
         self.config = config
         self.device = device
         self.best_net = None
+        self.match_count = 0   # matches played by this worker: every match gets its own game-id range (= its own random streams)
 
     def start(self, max_models=None):
         self.best_net = self._load(blob_path_of(self.config))
@@ -119,19 +122,49 @@ class EvaluateWorker:
             model_dir = self.next_generation_dir()
             ng_net = self._load(os.path.join(model_dir, NEXT_GENERATION_BLOB))
             logger.debug(f"start evaluate model {model_dir}")
-            if self.evaluate_model(ng_net):
+            if self.evaluate_model(ng_net, model_dir):
                 logger.debug(f"New Model become best model: {model_dir}")
-                shutil.copyfile(os.path.join(model_dir, NEXT_GENERATION_BLOB), blob_path_of(self.config))  # save_as_best_model
+                self.save_as_best_model(model_dir)
                 self.best_net = ng_net
-            shutil.rmtree(model_dir, ignore_errors=True)                                                  # remove_model, :115-121
+            self.remove_model(model_dir)
             done += 1
         return done
 
-    def evaluate_model(self, ng_net):
+    def save_as_best_model(self, model_dir):
+        """lib/model_helpler.py:22-28 save_as_best_model: the challenger becomes the best model for EVERY consumer -- the
+        engine-side blob, and the Keras-side model_best_config.json / model_best_weight.h5 the reference trainer
+        (worker/optimize.py load_model) and load_best_model_weight read -- when the trainer put them into the directory."""
+        rc = self.config.resource
+        shutil.copyfile(os.path.join(model_dir, NEXT_GENERATION_BLOB), blob_path_of(self.config))
+        for name, dst in ((rc.next_generation_model_config_filename, rc.model_best_config_path),
+                          (rc.next_generation_model_weight_filename, rc.model_best_weight_path)):
+            src = os.path.join(model_dir, name)
+            if os.path.exists(src):
+                shutil.copyfile(src, dst + ".tmp")
+                os.replace(dst + ".tmp", dst)
+
+    def remove_model(self, model_dir):
+        """worker/evaluate.py:115-121: the reference removes its two files and then the directory (os.rmdir fails, loudly,
+        on anything else in there); the mirror removes those two and the blob it added, nothing more."""
+        rc = self.config.resource
+        for name in (rc.next_generation_model_config_filename, rc.next_generation_model_weight_filename, NEXT_GENERATION_BLOB):
+            try:
+                os.remove(os.path.join(model_dir, name))
+            except FileNotFoundError:
+                pass
+        os.rmdir(model_dir)
+
+    def evaluate_model(self, ng_net, model_dir=""):
         """worker/evaluate.py:44-64"""
         game_num = int(_eval_field(self.config, "game_num", 200))
         replace_rate = float(_eval_field(self.config, "replace_rate", 0.55))
-        results, _ = play_match(self.config, self.best_net, ng_net, game_num, self.device)
+        # a fresh game-id range per match and a seed tied to the challenger's directory: consecutive matches (and
+        # restarts of the worker) do not replay the same dihedral / move-sampling streams
+        import zlib
+        seed = int(getattr(getattr(self.config, "b200", None), "seed", 0)) ^ zlib.crc32(os.path.basename(model_dir).encode())
+        results, _ = play_match(self.config, self.best_net, ng_net, game_num, self.device, seed=seed,
+                                first_game_id=self.match_count * 2 * game_num)
+        self.match_count += 1
         replace, winning_rate, counted = match_verdict(results, game_num, replace_rate)
         logger.debug(f"winning rate {winning_rate * 100:.1f}% after {counted} games")
         return replace

@@ -9,12 +9,14 @@ reference's entry points (manager.py:51-53, worker/self_play.py:28-41,64-93) and
 
 What differs by design: the reference forks ``multi_process_num`` Python workers that play one game
 each and talk to a Keras server through pipes; here ONE process per GPU drives ``b200.games_per_gpu``
-concurrent games that live entirely on the device (csrc/rz_engine.cu), and finished games are harvested
-in batches.  Across GPUs the game-id space is strided by rank and every rank writes its own files
+concurrent games that live entirely on the device (csrc/rz_engine.cu); finished games are harvested and
+written by a second host thread (``rz_engine_poll`` is the consumer end of a single-producer / single-consumer
+queue) while the first keeps the waves going, so the GPU never waits for the Python bookkeeping or the files
+(the reference overlaps the same work through its worker processes, worker/self_play.py:36-41).  Across GPUs the game-id space is strided by rank and every rank writes its own files
 (SURVEY 8(e)); the only collective is the weight broadcast.
 """
 import os
-import random
+import threading
 import time
 from datetime import datetime
 from logging import getLogger
@@ -57,19 +59,20 @@ NEXT_GENERATION_BLOB = "model_weight.rzblob.npy"  # next to model_weight.h5 in n
 def load_or_build_weights(config, net):
     """agent/api.py:102-115 load_model: with ``play.use_newest_next_generation_model`` (the default, config.py:166) the
     newest next-generation weights, else -- or if there are none -- the best weights; nothing there (or ``--new``):
-    build() + save_as_best.  The engine-side hand-off files are float32 .npy blobs."""
-    path = None if getattr(config.opts, "new", False) else weight_source_path(config)
-    h5_path = None if (path is not None or getattr(config.opts, "new", False)) else keras_h5_source_path(config)
+    build() + save_as_best.  The engine-side hand-off files are float32 .npy blobs written next to the
+    trainer's h5 files by tools/export_keras_weights.py; a model directory that holds ONLY h5 files is refused loudly
+    (reading HDF5 without libhdf5 cannot be pinned in this image, and start-up and hot reload must see the same files)."""
+    new = getattr(config.opts, "new", False)
+    path = None if new else weight_source_path(config)
     if path is not None:
         blob = np.load(path)
         logger.debug(f"loading weights from {path}")
-    elif h5_path is not None:
-        # no exported blob, but the trainer's own h5 file is there: read it directly (lib/h5lite.py -- unpinned reader, it
-        # raises on anything it does not understand rather than guessing)
-        from ..lib.h5lite import blob_from_keras_h5
-        blob = blob_from_keras_h5(config.model, h5_path)
-        logger.info(f"loaded Keras weights from {h5_path}")
     else:
+        h5_path = None if new else keras_h5_source_path(config)
+        if h5_path is not None:
+            raise RuntimeError(f"{h5_path} exists but its engine-side twin (*.rzblob.npy) does not: run "
+                               f"`python tools/export_keras_weights.py <model_config.json> {h5_path}` on the trainer side "
+                               f"(INTEGRATION.md section 4), or start with opts.new to random-initialise")
         path = blob_path_of(config)
         blob = M.weights_to_blob(config.model, M.build_random_weights(config.model, _b200(config).weight_seed))
         os.makedirs(os.path.dirname(path), exist_ok=True)
@@ -126,6 +129,8 @@ def weight_source_path(config):
 
 class SelfPlayWorker:
     MODEL_CHECK_INTERVAL_SEC = 60  # agent/api.py:80-82
+    WAVES_PER_RUN = 32             # waves between two control points of the driving thread (commands of the writer thread,
+                                   # weight-reload check, stop rules); rz_engine_run itself looks at the device every 8 waves
 
     def __init__(self, config, env=None, api=None, shared_var=None, worker_index=0, net=None, device=0, rank=0,
                  world_size=1):
@@ -148,8 +153,17 @@ class SelfPlayWorker:
         self.local_idx = 0
         self.game_idx = 0
         self.files_written = []
+        self.bytes_written = 0
         self.last_model_check_time = time.time()
         self.tensor_board = None
+        # the writer thread: harvests finished games (rz_engine_poll), keeps the reference's per-game bookkeeping and writes
+        # the files while the driving thread is inside rz_engine_run.  Engine calls it wants made (new simulation count,
+        # new resignation threshold) are queued and made by the driving thread between two runs: handles are not thread-safe.
+        self._writer = None
+        self._writer_stop = threading.Event()
+        self._writer_error = None
+        self._cmds = []
+        self._cmd_lock = threading.Lock()
 
     # -- reference helpers ---------------------------------------------------------------------------------
     def decide_simulation_num_per_move(self, idx):
@@ -161,6 +175,15 @@ class SelfPlayWorker:
             if idx >= min_idx:
                 ret = num
         return ret
+
+    def largest_simulation_num(self):
+        """The largest count decide_simulation_num_per_move can return during this run as far as it is known now: every
+        entry of the schedule and the current ``.force-sim`` value.  The engine's arenas are sized for it
+        (rz_engine_cfg.arena_simulation_num); a later, larger ``.force-sim`` makes the worker drain and re-create the
+        engine (_rebuild_engine)."""
+        nums = [int(num) for _, num in self.config.play.schedule_of_simulation_num_per_move]
+        nums.append(read_as_int(self.config.resource.force_simulation_num_file) or 0)
+        return max(nums + [1])
 
     @property
     def false_positive_rate(self):
@@ -181,13 +204,16 @@ class SelfPlayWorker:
         logger.debug(f"update resign_threshold: {old} -> {pc.resign_threshold}")
         self.false_positive_count_of_resign = 0
         self.resign_test_game_count = 0
-        self.engine.set_resign_threshold(pc.resign_threshold)
+        self._engine_cmd("set_resign_threshold", pc.resign_threshold)
 
-    def try_reload_model(self, force_check=False):
+    def try_reload_model(self, force_check=False, check_now=None):
         """agent/api.py:117-125 + lib/model_helpler.py digest logic: every 60 s look at the weight hand-off file
-        and, if its sha256 differs from the loaded weights, load it between two waves.  With several ranks, rank 0
-        decides and broadcasts flag + blob (NCCL), so that all GPUs switch at the same harvest point."""
-        if not force_check and time.time() - self.last_model_check_time < self.MODEL_CHECK_INTERVAL_SEC:
+        and, if its sha256 differs from the loaded weights, load it between two waves.  With several ranks every rank
+        must call this at the same control point (start() sees to that: the decision to check is part of the control
+        all-reduce); rank 0 reads the file and broadcasts flag + blob, so all GPUs switch at the same point."""
+        if check_now is None:
+            check_now = force_check or time.time() - self.last_model_check_time >= self.MODEL_CHECK_INTERVAL_SEC
+        if not check_now:
             return False
         self.last_model_check_time = time.time()
         # agent/api.py:117-125: the newest next-generation model if configured (and present), else the best model (the
@@ -206,15 +232,19 @@ class SelfPlayWorker:
         if self.world_size > 1:
             import torch
             import torch.distributed as dist
-            from ..parallel import broadcast_blob
-            flag = torch.tensor([1 if changed else 0], dtype=torch.int32, device=f"cuda:{self.device}")
+            from ..parallel import broadcast_blob, control_device
+            dev = control_device(self.device)
+            flag = torch.tensor([1 if changed else 0], dtype=torch.int32, device=dev)
             dist.broadcast(flag, src=0)
             if not int(flag.item()):
                 return False
-            t = broadcast_blob(self.config.model, blob, f"cuda:{self.device}")
-            torch.cuda.synchronize()
-            self.net.load_blob_dev(t)
-            self.net.digest = M.blob_digest(t.cpu().numpy())
+            t = broadcast_blob(self.config.model, blob, f"cuda:{self.device}" if dev != "cpu" else "cpu")
+            if dev != "cpu":
+                torch.cuda.synchronize()
+                self.net.load_blob_dev(t)
+                self.net.digest = M.blob_digest(t.cpu().numpy())
+            else:
+                self.net.load_blob(t.numpy())
             return True
         if changed:
             self.net.load_blob(blob)
@@ -233,33 +263,147 @@ class SelfPlayWorker:
         sims = self.decide_simulation_num_per_move(self.game_idx)
         cfg.play.simulation_num_per_move = sims
         ecfg = engine_cfg_from_play_config(cfg.play, games=b.games_per_gpu, seed=b.seed, eval_mode=EVAL_NET, net_impl=b.net_impl,
-                                           first_game_id=self.game_idx + self.rank, game_id_stride=self.world_size)
+                                           first_game_id=self.game_idx + self.rank, game_id_stride=self.world_size,
+                                           arena_simulation_num=max(sims, self.largest_simulation_num()),
+                                           warm_start=getattr(b, "warm_start", False))
         self.engine = Engine(ecfg, self.net, self.device)
+        profile = getattr(b, "warm_start_profile", None)
+        if profile is not None and getattr(b, "warm_start", False):
+            self.engine.set_warm_start_profile(profile)
 
-    def start(self, max_games=None, max_seconds=None, harvest_every=None):
-        """Runs until max_games finished / max_seconds elapsed (both None: forever, like the reference)."""
+    def _engine_cmd(self, name, *args):
+        """An engine call asked for by the per-game bookkeeping: made at once on the driving thread, queued for it when the
+        bookkeeping runs on the writer thread."""
+        if self._writer is not None and threading.current_thread() is self._writer:
+            with self._cmd_lock:
+                self._cmds.append((name, args))
+        else:
+            self._apply_cmd(name, args)
+
+    def _apply_cmd(self, name, args):
+        if name == "set_simulation_num":
+            if getattr(self, "_rebuilding", False):
+                return   # the engine being created takes its count from decide_simulation_num_per_move
+            try:
+                self.engine.set_simulation_num(*args)
+            except _cabi.RzError as ex:   # the arenas were sized for fewer simulations (a new, larger .force-sim)
+                logger.info(f"{ex}: draining the resident games and re-creating the engine")
+                self._rebuild_engine()
+        else:
+            getattr(self.engine, name)(*args)
+
+    def _apply_pending_cmds(self):
+        with self._cmd_lock:
+            cmds, self._cmds = self._cmds, []
+        for name, args in cmds:
+            self._apply_cmd(name, args)
+
+    def _rebuild_engine(self):
+        """The simulation count asked for does not fit the arenas: let the resident games finish (no slot starts another
+        one), harvest them, and create a new engine sized for the new count; game ids go on where the old engine stopped."""
+        threaded = self._writer is not None
+        self._rebuilding = True
+        try:
+            self.engine.set_max_games(1)
+            self.engine.run()                  # returns when every slot is idle
+            self._stop_writer()
+            self._finished_before = getattr(self, "_finished_before", 0) + self.engine.stats()["games_finished"]
+            self.engine.close()
+            self.engine = None
+            self._make_engine()
+        finally:
+            self._rebuilding = False
+        if threaded:
+            self._start_writer()
+
+    def _start_writer(self):
+        self._writer_stop.clear()
+        self._writer = threading.Thread(target=self._writer_loop, name=f"rz-writer-{self.rank}", daemon=True)
+        self._writer.start()
+
+    def _stop_writer(self):
+        """join the writer thread and take what is left in the engine's queue"""
+        if self._writer is not None:
+            self._writer_stop.set()
+            self._writer.join()
+            self._writer = None
+        if self._writer_error is not None:
+            err, self._writer_error = self._writer_error, None
+            raise err
+        self._harvest()
+
+    def _writer_loop(self):
+        try:
+            while not self._writer_stop.is_set():
+                if self._harvest() == 0:
+                    self._writer_stop.wait(0.02)
+        except BaseException as ex:  # reported by the driving thread at its next control point
+            self._writer_error = ex
+
+    def _control(self, want_check, time_up, games_done):
+        """One control point per run of WAVES_PER_RUN waves.  With several ranks the three decisions are all-reduced, so
+        that every rank checks for new weights (a collective) and leaves the loop at the same iteration: the check is
+        rank 0's decision, time is up when it is up anywhere, the game target is reached when it is reached everywhere."""
+        if self.world_size == 1:
+            return want_check, time_up or games_done
+        import torch
+        import torch.distributed as dist
+        from ..parallel import control_device
+        t = torch.tensor([int(want_check and self.rank == 0), int(time_up), int(not games_done)], dtype=torch.int32,
+                         device=control_device(self.device))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        check, up, not_done = (int(x) for x in t.tolist())
+        return bool(check), bool(up) or not not_done
+
+    def start(self, max_games=None, max_seconds=None, max_waves=None, threaded=True):
+        """Runs until max_games finished / max_seconds elapsed / max_waves executed (all None: forever, like the
+        reference).  Returns the number of games harvested by this call.  ``threaded=False`` harvests on the driving
+        thread between two runs (the round-1 behaviour, kept for A/B measurements)."""
         if self.engine is None:
             self._make_engine()
-        pdc = self.config.play_data
         t0 = time.time()
-        finished = 0
-        chunk = harvest_every or max(1, min(256, int(pdc.nb_game_in_file)))
-        while True:
-            target = finished + chunk
-            if max_games is not None:
-                target = min(target, max_games)
-            self.engine.run(finished_target=self.local_idx + (target - finished))
-            finished += self._harvest()
-            self.try_reload_model()
-            if max_games is not None and finished >= max_games:
-                break
-            if max_seconds is not None and time.time() - t0 >= max_seconds:
-                break
+        local0 = self.local_idx
+        self._finished_before = -self.engine.stats()["games_finished"]   # games finished before this call do not count
+        waves0 = self.engine.stats()["waves"]
+        waves_done = 0
+        if threaded:
+            self._start_writer()
+        try:
+            while True:
+                chunk = self.WAVES_PER_RUN if max_waves is None else min(self.WAVES_PER_RUN, max_waves - waves_done)
+                target = 0
+                if max_games is not None:
+                    # rz_engine_run's target is cumulative per engine
+                    target = max(1, max_games - self._finished_before)
+                eng = self.engine
+                eng.run(finished_target=target, max_waves=max(1, chunk))
+                if not threaded:
+                    self._harvest()
+                if self._writer_error is not None:
+                    raise self._writer_error
+                st = eng.stats()
+                waves_done = st["waves"] - waves0
+                finished = self._finished_before + st["games_finished"]
+                self._apply_pending_cmds()       # may re-create the engine
+                if self.engine is not eng:
+                    waves0 = -waves_done
+                want_check = time.time() - self.last_model_check_time >= self.MODEL_CHECK_INTERVAL_SEC
+                check, stop = self._control(want_check, max_seconds is not None and time.time() - t0 >= max_seconds,
+                                            (max_games is not None and finished >= max_games) or
+                                            (max_waves is not None and waves_done >= max_waves))
+                if check:
+                    self.try_reload_model(check_now=True)
+                if stop:
+                    break
+        finally:
+            if threaded:
+                self._stop_writer()
         self._flush_files(force=True)
-        return finished
+        return self.local_idx - local0
 
     def _log_scalars(self, g, n_plies, seconds_per_game):
-        """worker/self_play.py:125-129: self/time, self/turn (+ engine counters) under logs/tensorboard/self_play/workerNNN"""
+        """worker/self_play.py:125-129: self/time, self/turn, self/mcts_buffer_size (+ engine counters) under
+        logs/tensorboard/self_play/workerNNN"""
         if self.tensor_board is None:
             try:
                 from torch.utils.tensorboard import SummaryWriter
@@ -269,6 +413,8 @@ class SelfPlayWorker:
         if self.tensor_board:
             self.tensor_board.add_scalar("self/time", seconds_per_game, self.game_idx)
             self.tensor_board.add_scalar("self/turn", int(g.turn), self.game_idx)
+            # len(mtcs_info.var_p): the reference stores every prior under the key and its colour-swapped mirror (player.py:323)
+            self.tensor_board.add_scalar("self/mcts_buffer_size", 2 * int(g.table_nodes), self.game_idx)
             self.tensor_board.add_scalar("self/expansions", int(g.expansions), self.game_idx)
 
     def _harvest(self):
@@ -302,11 +448,8 @@ class SelfPlayWorker:
                 f.write(str(self.game_idx))
             new_sims = self.decide_simulation_num_per_move(self.game_idx)
             if new_sims and new_sims != pc.simulation_num_per_move:
-                try:
-                    self.engine.set_simulation_num(new_sims)
-                    pc.simulation_num_per_move = new_sims
-                except _cabi.RzError as ex:   # arenas were sized for fewer simulations: keep the current count
-                    logger.warning(str(ex))
+                pc.simulation_num_per_move = new_sims
+                self._engine_cmd("set_simulation_num", new_sims)
         return n_total
 
     def _finish_game(self, g):
@@ -369,6 +512,7 @@ class SelfPlayWorker:
                 write_play_rows(rows_path_of(path), G, len(self.buffer_games), P, pdc.save_policy_of_tau_1, self.config.play.change_tau_turn)
             logger.info(f"save play data to {path}")
             self.files_written.append(path)
+            self.bytes_written += os.path.getsize(path)
             self.buffer_games = []
             self.remove_play_data()
         if ggf and force:

@@ -1,7 +1,7 @@
 """TEST SUPPORT: writes the classic HDF5 on-disk structures (superblock v0, old-style groups = symbol-table message ->
 v1 B-tree -> SNOD nodes -> local heap, version-1 object headers, contiguous float32 datasets) that h5py emits by default,
 from a nested dict {name: ndarray | dict}.  Written from the published HDF5 file-format specification; NOT produced by
-libhdf5 -- see the "parity unpinned" note in reversi_zero_b200/lib/h5lite.py."""
+libhdf5 -- see the "parity unpinned" note in tools/h5lite.py."""
 import struct
 
 import numpy as np

@@ -35,6 +35,44 @@ def test_golden_vectors(golden_dir):
         assert np.array_equal(got, row)
 
 
+def test_dihedral_device_vs_golden(golden_dir):
+    """rz_dihedral_dev (the DEVICE code: __byte_perm / __brevll paths of rz_bitboard.cuh, used by the engine's leaf gather
+    and by the ingest kernel) against the reference's transforms, lib/bitboard.py:119-159, on the golden positions: all 8
+    values of t, t = flip * 4 + rot meaning flip_vertical first, then rot x rotate90 (agent/player.py:166-179,300-305)."""
+    g = np.load(os.path.join(golden_dir, "bitboard.npz"))
+    for name in ("own", "enemy"):
+        x = g[name]
+        got = {t: zb.dihedral_batch(x, t) for t in range(8)}
+        assert np.array_equal(got[0], x)
+        if name == "own":   # the golden transforms were generated from `own` by the unmodified reference
+            assert np.array_equal(got[1], g["rotate90"]) and np.array_equal(got[2], g["rotate180"])
+            assert np.array_equal(got[4], g["flip_vertical"])
+            # flip_diag_a1h8 (lib/bitboard.py:141-151) is not a member the players use directly; rotate90 is defined as
+            # flip_diag(flip_vertical(x)) (:154), so flip_diag(x) = rotate90(flip_vertical(x)) = t 5
+            assert np.array_equal(got[5], g["flip_diag"])
+        # composition, element by element, through the oracle functions (pinned to the same goldens in tests/test_oracle.py)
+        for t in range(8):
+            want = np.array([_compose(int(v), t) for v in x[:512]], dtype=U64)
+            assert np.array_equal(got[t][:512], want), t
+        # group structure on the full set: four rotations are the identity, the flip is an involution, rot^-1 = rot^3
+        assert np.array_equal(zb.dihedral_batch(got[3], 1), x) and np.array_equal(zb.dihedral_batch(got[4], 4), x)
+        assert np.array_equal(zb.dihedral_batch(got[6], 6), x)       # flip then rotate180 is an involution as well
+    # per-element t, ragged size, and agreement with the host twin the single-environment mirrors use
+    rng = np.random.default_rng(3)
+    x = g["own"][:1001]
+    t = rng.integers(0, 8, size=x.size, dtype=np.uint8)
+    assert np.array_equal(zb.dihedral_batch(x, t), np.array([zb.dihedral(int(v), int(tt)) for v, tt in zip(x, t)], dtype=U64))
+    assert zb.dihedral_batch(x[:0], 0).size == 0
+
+
+def _compose(v, t):
+    if t & 4:
+        v = ob.flip_vertical(v)
+    for _ in range(t & 3):
+        v = ob.rotate90(v)
+    return v
+
+
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 255, 256, 257, 100003])
 def test_ragged_sizes_vs_oracle(n):
     own, enemy, pos = positions(n + 5, n)

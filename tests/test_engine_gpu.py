@@ -122,28 +122,6 @@ def test_noise_statistics(golden_dir):
     eng.close()
 
 
-def test_warp_and_thread_tick_kernels_agree():
-    """the warp-per-game tick kernel (default) and the thread-per-slot cross-check kernel (RZ_TICK_IMPL=thread)
-    produce identical games, Dirichlet noise included (same Philox draws, same summation order)."""
-    pp = params(noise_eps=0.25, simulation_num_per_move=48, thinking_loop=2, required_visit_to_decide_action=20,
-                start_rethinking_turn=3)
-    out = {}
-    for impl in ("warp", "thread"):
-        os.environ["RZ_TICK_IMPL"] = impl
-        try:
-            eng = make_engine(pp, games=5, seed=77, max_games=8)
-            eng.run(finished_target=8)
-            gs = sorted(eng.poll(), key=lambda g: g["game_id"])
-            eng.close()
-        finally:
-            os.environ.pop("RZ_TICK_IMPL", None)
-        out[impl] = [(g["game_id"], g["winner"], g["expansions"], g["simulations"],
-                      [(p["own"], p["enemy"], p["action"], tuple(p["N"]), p["q"], p["loops"]) for p in g["plies"]]) for g in gs]
-        for g in gs:
-            replay_check(g)
-    assert out["warp"] == out["thread"]
-
-
 def test_search_with_real_network_matches_oracle():
     """Integration of the pieces the deterministic evaluator cannot exercise: the dihedral transform of the leaf
     batch (K3), the network, and the inverse-dihedral policy gather + re-normalisation at expansion.  mini.yml-sized

@@ -1,14 +1,14 @@
-"""lib/h5lite.py (PARITY UNPINNED -- see its header): the reader against files produced by the test
+"""tools/h5lite.py (a stand-alone conversion tool, NOT on the product path; PARITY UNPINNED -- see its header): the reader against files produced by the test
 writer of the same classic HDF5 structures, laid out like a Keras ``save_weights`` file of the reference's network
 (agent/model.py:28-72,95), and the whole chain h5 -> layers -> blob."""
 import numpy as np
 import pytest
 
 from reversi_zero_b200.agent import model as M
-from reversi_zero_b200.lib import h5lite
-
 import sys, os
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "support"))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import h5lite  # noqa: E402
 import h5_write  # noqa: E402
 
 
@@ -56,9 +56,10 @@ def test_rejects_what_it_does_not_understand(tmp_path):
         h5lite.read_datasets(str(p))
 
 
-def test_worker_finds_the_trainers_h5_when_no_blob_exists(tmp_path):
-    """load_or_build_weights (agent/api.py:102-115): with no exported blob but the reference's model_best_weight.h5 in
-    place, the weights come from the h5 file (host logic only: a stand-in for the device network records the blob)."""
+def test_worker_refuses_a_model_dir_with_only_h5_files(tmp_path):
+    """load_or_build_weights (agent/api.py:102-115): the product path takes exported blobs only; with the reference's
+    model_best_weight.h5 in place but no blob it must stop with the exporter hint instead of silently random-initialising
+    (or reading HDF5 with an unpinned parser) -- start-up and the 60 s hot reload look at the same files."""
     from reversi_zero_b200.config import Config
     from reversi_zero_b200.worker import self_play as sp
     cfg = Config(project_dir=str(tmp_path), data_dir=str(tmp_path / "data"))
@@ -72,6 +73,10 @@ def test_worker_finds_the_trainers_h5_when_no_blob_exists(tmp_path):
             self.blob = np.array(blob)
     net = FakeNet()
     assert sp.weight_source_path(cfg) is None and sp.keras_h5_source_path(cfg) == cfg.resource.model_best_weight_path
+    with pytest.raises(RuntimeError, match="export_keras_weights"):
+        sp.load_or_build_weights(cfg, net)
+    assert not os.path.exists(sp.blob_path_of(cfg))                 # nothing was invented or saved as "best"
+    # the stand-alone tool converts the file; with the blob next to it the worker starts from it
+    np.save(sp.blob_path_of(cfg), h5lite.blob_from_keras_h5(cfg.model, cfg.resource.model_best_weight_path))
     sp.load_or_build_weights(cfg, net)
     assert np.array_equal(net.blob, M.weights_to_blob(cfg.model, w))
-    assert not os.path.exists(sp.blob_path_of(cfg))                 # nothing was invented or saved as "best"

@@ -400,3 +400,147 @@ def test_player_mirror_takes_three_search_fields_from_the_self_play_section(tmp_
     assert (seen["cfg"].use_solver_turn_in_simulation, seen["cfg"].virtual_loss, seen["cfg"].simulation_num_per_move) == (48, 5, 400)
     P.ReversiPlayer(cfg, None)
     assert (seen["cfg"].use_solver_turn_in_simulation, seen["cfg"].virtual_loss, seen["cfg"].simulation_num_per_move) == (48, 5, 200)
+
+
+# ---- round 2: writer thread, arena sizing, engine re-creation (host logic with stand-in engines) -------------------------
+class StandInEngine(FakeEngine):
+    """Hands out `total` finished one-ply games, a few per run() call, through the same poll_raw() interface; records which
+    thread made every call so that the tests can check the driving-thread-only rule for engine calls."""
+    instances = []
+
+    def __init__(self, cfg=None, net=None, device=0, total=10 ** 9, per_run=3, sims_cap=10 ** 9):
+        import threading
+        super().__init__()
+        self.cfg, self.total, self.per_run, self.sims_cap = cfg, total, per_run, sims_cap
+        self.lock = threading.Lock()
+        self.queue, self.produced, self.waves = [], 0, 0
+        self.calls, self.closed, self.max_games = [], False, 0
+        StandInEngine.instances.append(self)
+
+    def _note(self, name, *args):
+        import threading
+        self.calls.append((name, threading.current_thread().name, args))
+
+    def run(self, finished_target=0, max_waves=0):
+        import time
+        self._note("run", finished_target, max_waves)
+        time.sleep(0.01)
+        self.waves += max_waves or 8
+        with self.lock:
+            n = min(self.per_run, self.total - self.produced) if not self.max_games else min(2, self.total - self.produced)
+            for _ in range(max(0, n)):
+                self.queue.append(self.produced)
+                self.produced += 1
+
+    def poll_raw(self):
+        with self.lock:
+            ids, self.queue = self.queue[:256], self.queue[256:]
+        n = len(ids)
+        G = (_cabi.Game * max(1, n))()
+        P = (_cabi.Ply * max(1, n))()
+        for i, gid in enumerate(ids):
+            G[i].game_id, G[i].first_ply, G[i].n_plies, G[i].winner, G[i].black_z = gid, i, 1, 1, 1
+            P[i].own, P[i].enemy, P[i].player, P[i].recorded, P[i].action = 0x0000000810000000, 0x0000001008000000, 1, 1, 19
+            P[i].n_visit[19] = 7
+        return G, n, P, n
+
+    def stats(self):
+        return dict(games_finished=self.produced, waves=self.waves)
+
+    def set_simulation_num(self, n):
+        self._note("set_simulation_num", n)
+        if n > self.sims_cap:
+            raise _cabi.RzError("simulation count %d exceeds the arenas sized at creation" % n)
+
+    def set_max_games(self, n):
+        self._note("set_max_games", n)
+        self.max_games = n
+
+    def set_resign_threshold(self, t):
+        self._note("set_resign_threshold", t)
+        super().set_resign_threshold(t)
+
+    def close(self):
+        self.closed = True
+
+
+def test_writer_thread_harvests_while_the_driver_runs(tmp_path):
+    """start(): finished games are harvested and written by the writer thread while the driving thread is inside
+    engine.run(); engine calls asked for by the bookkeeping (new simulation count from the schedule, new resignation
+    threshold from the tuner) are made by the DRIVING thread between two runs, never by the writer thread."""
+    import glob
+    import json
+    import threading
+    cfg, w = make_worker(tmp_path)
+    cfg.play_data.update(dict(nb_game_in_file=5, max_file_num=1000, enable_ggf_data=False, drop_draw_game_rate=0))
+    cfg.play.schedule_of_simulation_num_per_move = [[0, 8], [20, 50]]
+    cfg.play.simulation_num_per_move = 8
+    w.engine = StandInEngine(total=10 ** 9, per_run=4)
+    w.resign_test_game_count, w.false_positive_count_of_resign = 99, 0     # the next test game triggers the tuner
+    n = w.start(max_games=40)
+    assert n >= 40 and n == w.local_idx == w.engine.produced               # nothing lost between queue, thread and files
+    files = sorted(glob.glob(os.path.join(cfg.resource.play_data_dir, "play_*.json")))
+    assert sum(len(json.load(open(f))) for f in files) == 8 * n and w.bytes_written == sum(os.path.getsize(f) for f in files)
+    assert int(open(cfg.resource.self_play_game_idx_file).read()) == n
+    me = threading.current_thread().name
+    assert all(thread == me for name, thread, _ in w.engine.calls)
+    assert ("set_simulation_num", me, (50,)) in w.engine.calls and cfg.play.simulation_num_per_move == 50
+    assert any(name == "set_resign_threshold" for name, _, _ in w.engine.calls)
+    assert w._writer is None                                               # joined
+    # the single-threaded mode gives the same bookkeeping
+    cfg2, w2 = make_worker(tmp_path / "b")
+    cfg2.play_data.update(dict(nb_game_in_file=5, max_file_num=1000, enable_ggf_data=False))
+    w2.engine = StandInEngine(total=10 ** 9, per_run=4)
+    assert w2.start(max_games=12, threaded=False) >= 12 and w2.local_idx == w2.engine.produced
+
+
+def test_writer_thread_errors_reach_the_driver(tmp_path):
+    cfg, w = make_worker(tmp_path)
+    w.engine = StandInEngine(per_run=2)
+    w._finish_game = lambda g: (_ for _ in ()).throw(ValueError("boom"))
+    with pytest.raises(ValueError, match="boom"):
+        w.start(max_games=50)
+
+
+def test_arenas_are_sized_for_the_largest_simulation_count(tmp_path, monkeypatch):
+    """with the default schedule [(0,8),(300,50),(2000,200)] a fresh run starts at 8 simulations; the
+    engine must be created with room for 200 (rz_engine_cfg.arena_simulation_num) so that the schedule can take effect."""
+    import reversi_zero_b200.worker.self_play as sp
+    StandInEngine.instances.clear()
+    monkeypatch.setattr(sp, "Engine", StandInEngine)
+    cfg = Config(project_dir=str(tmp_path), data_dir=str(tmp_path / "data"))
+    w = SelfPlayWorker(cfg, net=object())
+    assert w.largest_simulation_num() == 200
+    w._make_engine()
+    ecfg = StandInEngine.instances[-1].cfg
+    assert (ecfg.simulation_num_per_move, ecfg.arena_simulation_num) == (8, 200)
+    with open(cfg.resource.force_simulation_num_file, "wt") as f:
+        f.write("640")
+    assert w.largest_simulation_num() == 640
+    w._make_engine()
+    ecfg = StandInEngine.instances[-1].cfg
+    assert (ecfg.simulation_num_per_move, ecfg.arena_simulation_num) == (640, 640)
+
+
+def test_engine_is_drained_and_recreated_when_a_new_force_sim_exceeds_the_arenas(tmp_path, monkeypatch):
+    """A `.force-sim` value larger than anything known at creation: the worker lets the resident games finish
+    (set_max_games(1), run until idle), harvests them, and creates a new engine sized for the new count -- it does not
+    swallow the error and keep the old count."""
+    import reversi_zero_b200.worker.self_play as sp
+    StandInEngine.instances.clear()
+    monkeypatch.setattr(sp, "Engine", lambda cfg, net, dev: StandInEngine(cfg, net, dev, per_run=3, sims_cap=cfg.arena_simulation_num))
+    cfg = Config(project_dir=str(tmp_path), data_dir=str(tmp_path / "data"))
+    cfg.play_data.update(dict(nb_game_in_file=4, enable_ggf_data=False))
+    cfg.play.schedule_of_simulation_num_per_move = [[0, 8]]
+    w = SelfPlayWorker(cfg, net=object())
+    w._make_engine()
+    first = w.engine
+    assert first.cfg.arena_simulation_num == 8
+    with open(cfg.resource.force_simulation_num_file, "wt") as f:
+        f.write("300")
+    n = w.start(max_games=30)
+    second = w.engine
+    assert second is not first and first.closed and ("set_max_games", "MainThread", (1,)) in first.calls
+    assert (second.cfg.simulation_num_per_move, second.cfg.arena_simulation_num) == (300, 300)
+    assert second.cfg.first_game_id == first.produced                      # ids go on where the old engine stopped
+    assert n == first.produced + second.produced >= 30 and w.local_idx == n

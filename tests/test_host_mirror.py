@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in sorted(declared) if not hasattr(lib, n)]
     assert not missing, f"symbols declared but not exported: {missing}"
     assert declared == set(_cabi.SIGNATURES), declared ^ set(_cabi.SIGNATURES)
-    assert lib.rz_abi_version() == 1
+    assert lib.rz_abi_version() == 2
 
 
 def test_host_twins_vs_golden(golden_dir):

@@ -2,6 +2,10 @@
 ``model_weight.h5`` / ``model_best_weight.h5``, agent/model.py:82-101) -- pure Python + numpy, because neither h5py nor
 libhdf5 exists in the target image.
 
+NOT ON THE PRODUCT PATH (round 2): the self-play worker takes float32 blobs only (tools/export_keras_weights.py writes them
+on the trainer side, where Keras/h5py exist) and refuses a model directory that holds nothing but h5 files.  This reader is
+kept as a stand-alone conversion tool (`python tools/h5lite.py <model_weight.h5> <out.rzblob.npy> [filters blocks value_fc]`).
+
 PARITY UNPINNED: no HDF5 file written by libhdf5 is available where this was built, so the reader has only been checked
 against files produced by this repo's own writer of the same on-disk structures (tests/support/h5_write.py).  It reads
 the classic layout h5py emits by default (``libver='earliest'``): superblock version 0 or 1, old-style groups (symbol
@@ -201,5 +205,17 @@ def keras_layers_from_h5(datasets):
 
 def blob_from_keras_h5(mc, path):
     """model_weight.h5 of the reference (Keras save_weights) -> the float32 blob rz_net_load_weights takes."""
-    from ..agent import model as M
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "reversi-alpha-zero_b200"))
+    from reversi_zero_b200.agent import model as M
     return M.weights_to_blob(mc, M.weights_from_keras_layers(mc, keras_layers_from_h5(read_datasets(path))))
+
+
+if __name__ == "__main__":
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "reversi-alpha-zero_b200"))
+    from reversi_zero_b200.agent import model as M
+    f, b, v = (int(x) for x in sys.argv[3:6]) if len(sys.argv) >= 6 else (256, 10, 256)
+    np.save(sys.argv[2], blob_from_keras_h5(M.ModelConfig(cnn_filter_num=f, res_layer_num=b, value_fc_size=v), sys.argv[1]))
