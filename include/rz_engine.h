@@ -131,6 +131,11 @@ int rz_net_predict_dev(rz_net* net, const uint64_t* own, const uint64_t* enemy, 
  * tower[n][64 pixels][256 channels] (pixel = y*8+x) so tests can localise a numerical difference. */
 int rz_net_debug_tower_dev(rz_net* net, const uint64_t* own, const uint64_t* enemy, float* policy, float* value,
                            float* tower, size_t n, void* stream);
+/* same, plus the head outputs BEFORE softmax / tanh -- policy_logits[n][64] (the input of the policy_out softmax,
+ * agent/model.py:47) and value_logit[n] (the input of the value_out tanh, :55) -- so that the north-star tolerance
+ * ("policy/value logits within 1e-3") can be asserted on the logits themselves; tower may be NULL. */
+int rz_net_debug_heads_dev(rz_net* net, const uint64_t* own, const uint64_t* enemy, float* policy, float* value,
+                           float* tower, float* policy_logits, float* value_logit, size_t n, void* stream);
 /* ReversiModelAPI.predict (agent/api.py:30-45): planes uint8 [n][2][8][8] with values {0,1}, host
  * buffers in, policy[n][64] / value[n] host buffers out. */
 int rz_net_predict(rz_net* net, const uint8_t* planes, float* policy, float* value, size_t n, int impl);

@@ -47,6 +47,80 @@ def forward(w, planes, n_res, return_tower=False, dtype=torch.float32):
     return policy.numpy(), value.numpy()
 
 
+def _fold(w, name):
+    g, b, m, v = (torch.from_numpy(w[f"{name}.bn_{p}"]) for p in ("gamma", "beta", "mean", "var"))
+    s = g / torch.sqrt(v + BN_EPS)
+    return s.view(1, -1, 1, 1), ((torch.from_numpy(w[f"{name}.bias"]) - m) * s + b).view(1, -1, 1, 1)
+
+
+@torch.no_grad()
+def forward_fp16_operands(w, planes, n_res, round_weights=True, round_acts=True):
+    """The SAME network evaluated the way the tcgen05 tower is specified to evaluate it: convolution operands rounded
+    to fp16 (round-to-nearest-even; weights of all 1 + 2R convolutions, activations of the 2R tower convolutions -- the
+    first layer's {0,1} planes are exact), products and sums exact (fp64 here; the tensor core accumulates in fp32),
+    folded BatchNorm / residual stream / heads in fp32.  The difference between this and `forward` is the error the
+    *number format* costs; whatever the kernel adds on top is the kernel's own (tools/nn_diag.py prints both).
+    Returns policy, value, logits, value_logit, tower."""
+    def h(t):
+        return t.half().float()
+
+    def conv(x, name, ra):
+        k = torch.from_numpy(w[f"{name}.kernel"]).permute(3, 2, 0, 1).contiguous()
+        k = h(k) if round_weights else k
+        x = h(x) if (ra and round_acts) else x
+        s, sh = _fold(w, name)
+        return F.conv2d(x.double(), k.double(), padding=1).float() * s + sh
+
+    x = F.relu(conv(torch.from_numpy(np.ascontiguousarray(planes)).float(), "conv0", False))
+    for i in range(n_res):
+        y = F.relu(conv(x, f"res{i}.conv1", True))
+        x = F.relu(conv(y, f"res{i}.conv2", True) + x)
+    return heads(w, x)
+
+
+@torch.no_grad()
+def heads(w, x):
+    """policy / value heads (agent/model.py:43-56) in fp32 from a tower output x (N, C, 8, 8)"""
+    def c1(name):
+        k = torch.from_numpy(w[f"{name}.kernel"]).permute(3, 2, 0, 1).contiguous()
+        s, sh = _fold(w, name)
+        return F.relu(F.conv2d(x, k) * s + sh).reshape(x.shape[0], -1)
+    logits = c1("policy_conv") @ torch.from_numpy(w["policy_fc.kernel"]) + torch.from_numpy(w["policy_fc.bias"])
+    v = F.relu(c1("value_conv") @ torch.from_numpy(w["value_fc1.kernel"]) + torch.from_numpy(w["value_fc1.bias"]))
+    pre = (v @ torch.from_numpy(w["value_fc2.kernel"]) + torch.from_numpy(w["value_fc2.bias"])).reshape(-1)
+    return torch.softmax(logits, 1).numpy(), torch.tanh(pre).numpy(), logits.numpy(), pre.numpy(), x.numpy()
+
+
+@torch.no_grad()
+def forward_logits(w, planes, n_res):
+    """fp32 reference with the head outputs before softmax / tanh: policy, value, logits, value_logit, tower"""
+    return forward_fp16_operands(w, planes, n_res, round_weights=False, round_acts=False)
+
+
+@torch.no_grad()
+def calibrate_bn(w, planes, n_res):
+    """Trained-like weights for the tolerance tests: the BatchNormalization moving statistics of every layer are set to
+    the statistics of that layer's own pre-activation over `planes` (what training leaves behind: every layer's output is
+    normalised, then scaled / shifted by gamma / beta), keeping whatever gamma, beta and biases `w` has.  In place."""
+    x = torch.from_numpy(np.ascontiguousarray(planes)).float()
+
+    def layer(x, name, res=None):
+        k = torch.from_numpy(w[f"{name}.kernel"]).permute(3, 2, 0, 1).contiguous()
+        y = F.conv2d(x, k, torch.from_numpy(w[f"{name}.bias"]), padding=k.shape[-1] // 2)
+        w[f"{name}.bn_mean"] = y.mean(dim=(0, 2, 3)).numpy().copy()
+        w[f"{name}.bn_var"] = y.var(dim=(0, 2, 3), unbiased=False).numpy().copy()
+        s, sh = _fold(w, name)
+        y = F.conv2d(x, k, padding=k.shape[-1] // 2) * s + sh
+        return F.relu(y if res is None else y + res)
+
+    x = layer(x, "conv0")
+    for i in range(n_res):
+        x = layer(layer(x, f"res{i}.conv1"), f"res{i}.conv2", x)
+    layer(x, "policy_conv")
+    layer(x, "value_conv")
+    return w
+
+
 def planes_from_bitboards(own, enemy):
     """(N,) u64 pairs -> (N,2,8,8) uint8 planes [own, enemy], plane[y][x] = bit y*8+x (bit_to_array)."""
     own = np.asarray(own, np.uint64).reshape(-1, 1)

@@ -481,7 +481,9 @@ struct WCtx {
                 const bool b = sl.env.next_player == 1;
                 begin_ply(b ? sl.env.black : sl.env.white, b ? sl.env.white : sl.env.black, sl.env.next_player);
                 if (sl.phase == PH_SEARCH) {
-                    const uint32_t part = (uint32_t)(u01(r0.y) * (double)c.S) + 1u;
+                    // at least two simulations: the first one only expands the root, and a recorded ply needs a visit
+                    uint32_t part = (uint32_t)(u01(r0.y) * (double)c.S) + 1u;
+                    if (part < 2u) part = 2u;
                     sl.sims_target = part < (uint32_t)c.S ? part : (uint32_t)c.S;
                 }
             }

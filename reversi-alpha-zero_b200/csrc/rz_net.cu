@@ -306,6 +306,13 @@ int rz_net_debug_tower_dev(rz_net* net, const uint64_t* own, const uint64_t* ene
     return net_forward_tc(net, own, enemy, policy, value, n, (cudaStream_t)stream, tower);
 }
 
+int rz_net_debug_heads_dev(rz_net* net, const uint64_t* own, const uint64_t* enemy, float* policy, float* value, float* tower,
+                           float* policy_logits, float* value_logit, size_t n, void* stream) {
+    RZ_REQUIRE(net && own && enemy && policy && value && policy_logits && value_logit, "rz_net_debug_heads_dev: null pointer");
+    if (!net->loaded) { set_error("rz_net: weights not loaded"); return RZ_ESTATE; }
+    return net_forward_tc(net, own, enemy, policy, value, n, (cudaStream_t)stream, tower, nullptr, policy_logits, value_logit);
+}
+
 int rz_net_predict(rz_net* net, const uint8_t* planes, float* policy, float* value, size_t n, int impl) {
     RZ_REQUIRE(net && (n == 0 || (planes && policy && value)), "rz_net_predict: null pointer");
     if (n == 0) return RZ_OK;

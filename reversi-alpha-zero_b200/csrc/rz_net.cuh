@@ -42,7 +42,8 @@ int net_forward_counted(rz_net* net, const uint64_t* own, const uint64_t* enemy,
                         const uint32_t* count_dev, size_t max_n, int impl, cudaStream_t stream);
 int net_forward_tc(rz_net* net, const uint64_t* own, const uint64_t* enemy, float* policy, float* value, size_t n,
                    cudaStream_t stream, float* dbg_tower /* nullable: [n][64][256] fp32 tower output */,
-                   const uint32_t* n_dev = nullptr /* nullable: actual batch size in device memory (<= n) */);
+                   const uint32_t* n_dev = nullptr /* nullable: actual batch size in device memory (<= n) */,
+                   float* dbg_logits = nullptr /* nullable: [n][64] policy logits */, float* dbg_vlogit = nullptr /* nullable: [n] */);
 int net_pack_tc(rz_net* net, cudaStream_t stream);
 int net_forward(rz_net* net, const uint64_t* own, const uint64_t* enemy, float* policy, float* value, size_t n, int impl,
                 cudaStream_t stream);

@@ -202,6 +202,8 @@ struct Params {
     float* policy;
     float* value;
     float* dbg_tower;  // nullable
+    float* dbg_logits; // nullable: [n][64] policy logits (before the softmax)
+    float* dbg_vlogit; // nullable: [n] value before the tanh
     uint32_t n;
     const uint32_t* n_dev;  // nullable: batch size produced on the device (engine waves)
     int n_layers;  // 1 + 2R
@@ -212,7 +214,11 @@ struct Params {
 // stage from L2 and multicast it into both CTAs' shared memory (L2 -> SM weight traffic halves); MMAs, TMEM and the
 // epilogue stay per-CTA (cta_group::1).  A stage may be refilled only after BOTH CTAs' MMAs have read it, so the
 // `empty` barriers count CL commits (each MMA thread commits to every CTA of the cluster).
-template <int CL>
+// EXP != 0 are MEASUREMENT variants (RZ_TOWER_EXPERIMENT, tools/nn_bench.py; results are garbage): 1 = the epilogue only
+// keeps the barrier protocol (no accumulator read-out, no BN / ReLU, no operand stores): the time of the MMA stream alone,
+// i.e. what a perfect overlap of epilogue and MMA could reach; 2 = the MMA thread issues no MMAs (barriers only): the time
+// of the epilogues alone.
+template <int CL, int EXP = 0>
 __global__ void __launch_bounds__(kThreads, 1) net_tower_kernel(const Params pp) {
     Params p = pp;
     if (p.n_dev) p.n = *p.n_dev;
@@ -302,10 +308,12 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_kernel(const Params pp)
                                 mbar_wait(bar_full(stage), phase);
                                 tc_fence_after();
                                 const uint32_t b_st = base + kOffW + stage * kStageBytes;
+                                if (EXP != 2) {
 #pragma unroll
-                                for (uint32_t j = 0; j < 4; ++j)
-                                    umma_f16(tm_acc, smem_desc(a_tap + (kb * 8 + 2 * j) * kActCg, kActCg, kActSlot),
-                                             smem_desc(b_st + 2 * j * 4096, 4096, 128), kIdesc, (tap | kb | j) != 0);
+                                    for (uint32_t j = 0; j < 4; ++j)
+                                        umma_f16(tm_acc, smem_desc(a_tap + (kb * 8 + 2 * j) * kActCg, kActCg, kActSlot),
+                                                 smem_desc(b_st + 2 * j * 4096, 4096, 128), kIdesc, (tap | kb | j) != 0);
+                                }
                                 if (CL == 1) umma_commit(bar_empty(stage)); else umma_commit_mc(bar_empty(stage), kMask);
                                 if (++stage == kStages) { stage = 0; phase ^= 1; }
                             }
@@ -377,6 +385,10 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_kernel(const Params pp)
                 mbar_wait(bar_acc, acc_par);
                 acc_par ^= 1;
                 tc_fence_after();
+                if (EXP == 1) {
+                    if (l != L - 1) { tc_fence_before(); mbar_arrive(bar_a); }
+                    continue;
+                }
                 const bool is_conv2 = l > 0 && (l & 1) == 0;   // second conv of a block: add the skip connection
                 const bool keep_res = l == 0 || is_conv2;      // block output: keep fp32 copy in TMEM
                 const bool last = l == L - 1;
@@ -507,6 +519,10 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_kernel(const Params pp)
                 if (pos0 + b < p.n) {
                     p.policy[(size_t)(pos0 + b) * 64 + lane] = e0 / s;
                     p.policy[(size_t)(pos0 + b) * 64 + 32 + lane] = e1 / s;
+                    if (p.dbg_logits) {
+                        p.dbg_logits[(size_t)(pos0 + b) * 64 + lane] = l0;
+                        p.dbg_logits[(size_t)(pos0 + b) * 64 + 32 + lane] = l1;
+                    }
                 }
             } else if (ew < 4) {  // value Dense(V -> 1) + tanh, one warp per board
                 const int b = ew - 2;
@@ -514,7 +530,11 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_kernel(const Params pp)
                 for (int j = lane; j < p.V; j += 32) acc = fmaf(fc1[b * kMaxV + j], __ldg(p.blob + p.off_value_fc2_k + j), acc);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                if (lane == 0 && pos0 + b < p.n) p.value[pos0 + b] = tanhf(acc + __ldg(p.blob + p.off_value_fc2_b));
+                if (lane == 0 && pos0 + b < p.n) {
+                    const float pre = acc + __ldg(p.blob + p.off_value_fc2_b);
+                    p.value[pos0 + b] = tanhf(pre);
+                    if (p.dbg_vlogit) p.dbg_vlogit[pos0 + b] = pre;
+                }
             }
             // the next tile's layer-0 operand build only touches the A0 region, whose last reader (this tile's
             // layer-0 MMAs) completed before the first bar_acc of this tile
@@ -557,14 +577,18 @@ int net_pack_tc(rz_net* net, cudaStream_t stream) {
 }
 
 int net_forward_tc(rz_net* net, const uint64_t* own, const uint64_t* enemy, float* policy, float* value, size_t n, cudaStream_t stream,
-                   float* dbg_tower, const uint32_t* n_dev) {
+                   float* dbg_tower, const uint32_t* n_dev, float* dbg_logits, float* dbg_vlogit) {
     RZ_REQUIRE(net->cfg.filters == 256, "tcgen05 tower requires 256 filters");
     RZ_REQUIRE(net->cfg.value_fc <= (int)tc::kMaxV, "tcgen05 tower supports value_fc_size <= %u", tc::kMaxV);
     RZ_REQUIRE(n < (1ull << 31), "batch too large");
-    static int cluster = -1;
+    static int cluster = -1, experiment = 0;
     if (cluster < 0) {
         const char* cs = getenv("RZ_TOWER_CLUSTER");
         cluster = (cs && atoi(cs) == 1) ? 1 : 2;
+        const char* ex = getenv("RZ_TOWER_EXPERIMENT");
+        experiment = ex ? atoi(ex) : 0;
+        RZ_CUDA_TRY(cudaFuncSetAttribute(tc::net_tower_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemAlloc));
+        RZ_CUDA_TRY(cudaFuncSetAttribute(tc::net_tower_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemAlloc));
         RZ_CUDA_TRY(cudaFuncSetAttribute(tc::net_tower_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemAlloc));
         RZ_CUDA_TRY(cudaFuncSetAttribute(tc::net_tower_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemAlloc));
     }
@@ -574,6 +598,7 @@ int net_forward_tc(rz_net* net, const uint64_t* own, const uint64_t* enemy, floa
     p.off_value_conv = net->off_value_conv; p.off_value_fc1_k = net->off_value_fc1_k; p.off_value_fc1_b = net->off_value_fc1_b;
     p.off_value_fc2_k = net->off_value_fc2_k; p.off_value_fc2_b = net->off_value_fc2_b;
     p.own = own; p.enemy = enemy; p.policy = policy; p.value = value; p.dbg_tower = dbg_tower;
+    p.dbg_logits = dbg_logits; p.dbg_vlogit = dbg_vlogit;
     p.n = (uint32_t)n; p.n_dev = n_dev; p.n_layers = 1 + 2 * net->cfg.res_blocks; p.V = net->cfg.value_fc;
     const uint32_t ntiles = (uint32_t)((n + 1) / 2);
     uint32_t grid = ntiles < (uint32_t)num_sms() ? ntiles : (uint32_t)num_sms();
@@ -587,7 +612,9 @@ int net_forward_tc(rz_net* net, const uint64_t* own, const uint64_t* enemy, floa
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        RZ_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::net_tower_kernel<2>, p));
+        if (experiment == 1) RZ_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::net_tower_kernel<2, 1>, p));
+        else if (experiment == 2) RZ_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::net_tower_kernel<2, 2>, p));
+        else RZ_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc::net_tower_kernel<2>, p));
     }
     RZ_LAUNCH_CHECK();
     return RZ_OK;

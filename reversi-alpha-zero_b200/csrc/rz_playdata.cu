@@ -16,6 +16,8 @@ namespace rz {
 // scientific with a sign and at least two exponent digits.
 static void append_pyfloat(std::string& out, double v) {
     if (v == 0.0) { out += "0.0"; return; }
+    if (v != v) { out += "NaN"; return; }                       // json.dumps(float("nan")) (allow_nan=True, the default)
+    if (v - v != 0.0) { out += v > 0 ? "Infinity" : "-Infinity"; return; }
     char buf[64];
     auto r = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::scientific);
     *r.ptr = 0;

@@ -60,6 +60,14 @@ class Net:
                                                         C.c_void_p(policy_t.data_ptr()), C.c_void_p(value_t.data_ptr()),
                                                         C.c_void_p(tower_t.data_ptr()), n, stream_ptr), "rz_net_debug_tower_dev")
 
+    def debug_heads_dev(self, own_t, enemy_t, policy_t, value_t, logits_t, vlogit_t, n, tower_t=None, stream_ptr=None):
+        """tcgen05 path with the head outputs before softmax / tanh (and optionally the fp32 tower output)"""
+        _cabi.check(_cabi.lib().rz_net_debug_heads_dev(self._h, C.c_void_p(own_t.data_ptr()), C.c_void_p(enemy_t.data_ptr()),
+                                                        C.c_void_p(policy_t.data_ptr()), C.c_void_p(value_t.data_ptr()),
+                                                        C.c_void_p(tower_t.data_ptr()) if tower_t is not None else None,
+                                                        C.c_void_p(logits_t.data_ptr()), C.c_void_p(vlogit_t.data_ptr()), n, stream_ptr),
+                    "rz_net_debug_heads_dev")
+
     def close(self):
         if self._h:
             _cabi.lib().rz_net_destroy(self._h)

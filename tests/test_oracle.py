@@ -270,3 +270,54 @@ def test_evaluation_match_exact_vs_reference(golden_dir):
             ng_is_black = not ref["best_is_black"]
             ng_win = None if e.winner == 3 else int((e.winner == 1) == ng_is_black)
             assert ng_win == ref["ng_win"], (variant, i)
+
+
+def test_mcts_k8_positions_vs_reference(golden_dir):
+    """K = 8 + Dirichlet noise at every root selection: 12 roots from the opening to the endgame (tests/golden/mcts_k8.json,
+    the UNMODIFIED ReversiPlayer, 100 repetitions each).  The reference's interleaving of its eight coroutines depends on
+    asyncio timers, the oracle's wave model is deterministic, so the comparison is statistical: mean root visit fractions,
+    mean Q of the most visited move, mean network evaluations per search."""
+    ref = _load(golden_dir, "mcts_k8.json")["positions"]
+    assert len(ref) >= 10
+    reps = 50
+    for p in ref:
+        pp = mcts.PlayParams(simulation_num_per_move=p["sims"], parallel_search_num=8, noise_eps=0.25, change_tau_turn=0,
+                             c_puct=p["c_puct"], resign_threshold=None)
+        acc, q_top, rows = np.zeros(64), 0.0, 0
+        for r in range(reps):
+            game = mcts.SelfPlayGame(pp, nn.FakeNetAPI(), seed=1234, game_id=r)
+            game.search(p["own"], p["enemy"], 1)
+            node = game.table[(p["own"], p["enemy"])]
+            acc += node.N / node.N.sum()
+            a = int(np.argmax(node.N))
+            q_top += float(node.W[a] / (node.N[a] + 1e-5))
+            rows += game.n_expand
+        mine, theirs = acc / reps, np.array(p["mean_visit_frac"])
+        assert set(np.nonzero(mine)[0]) == set(np.nonzero(theirs)[0]), p["turn"]
+        assert np.abs(mine - theirs).max() < 0.03, (p["turn"], np.abs(mine - theirs).max())
+        assert abs(q_top / reps - p["mean_q_of_most_visited"]) < 0.05, (p["turn"], q_top / reps, p["mean_q_of_most_visited"])
+        assert abs(rows / reps - p["mean_expansions"]) <= 0.03 * p["mean_expansions"] + 0.5, (p["turn"], rows / reps, p["mean_expansions"])
+
+
+def test_mcts_k8_whole_game_distributions_vs_reference(golden_dir):
+    """whole self-play games at K = 8 (50 simulations per move, tau turn 4, noise): plies per game, network evaluations per
+    game, final disc difference and the winner split of the oracle against 80 games of the unmodified reference loop
+    (worker/self_play.py:139-175 + agent/player.py) -- the quantities the throughput metric is built on."""
+    ref = _load(golden_dir, "mcts_k8.json")["games"]
+    g = ref["games"]
+    pp = mcts.PlayParams(simulation_num_per_move=ref["sims"], parallel_search_num=8, noise_eps=ref["noise_eps"],
+                         change_tau_turn=ref["change_tau_turn"], c_puct=ref["c_puct"], resign_threshold=None)
+    n = 40
+    mine = [mcts.SelfPlayGame(pp, nn.FakeNetAPI(), seed=4321, game_id=i).play() for i in range(n)]
+
+    def stats(plies, exps, dd):
+        return np.mean(plies), np.mean(exps), np.mean(dd), np.std(dd)
+    m_pl, m_ex, m_dd, s_dd = stats([len(x.plies) for x in mine], [x.n_expand for x in mine],
+                                   [bin(x.env.black).count("1") - bin(x.env.white).count("1") for x in mine])
+    r_pl, r_ex, r_dd, r_sd = stats([x["plies"] for x in g], [x["expansions"] for x in g], [x["disc_diff"] for x in g])
+    se_pl = np.std([x["plies"] for x in g]) * np.sqrt(1 / n + 1 / len(g))
+    se_ex = np.std([x["expansions"] for x in g]) * np.sqrt(1 / n + 1 / len(g))
+    assert abs(m_pl - r_pl) < 4 * se_pl + 0.5, (m_pl, r_pl)
+    assert abs(m_ex - r_ex) < 4 * se_ex, (m_ex, r_ex)                       # expansions per game: what games/s is derived from
+    assert abs(m_dd - r_dd) < 4 * r_sd * np.sqrt(1 / n + 1 / len(g)), (m_dd, r_dd)
+    assert 0.6 < s_dd / r_sd < 1.6

@@ -92,3 +92,19 @@ def test_reference_trainer_loads_our_files(tmp_path):
     assert np.allclose(policies.sum(axis=1), 1.0)
     # first record = first ply of black from the start position, identity symmetry
     assert states[0, 0].sum() == 2 and states[0, 1].sum() == 2 and states[0, 0, 3, 4] == 1
+
+
+def test_ply_without_visits_does_not_crash(tmp_path):
+    """A recorded ply whose root has no visited move (possible only for a truncated search, e.g. one simulation): the
+    reference's n / np.sum(n) gives NaN and json.dumps writes `NaN`; the C writer must do the same instead of walking off a
+    null pointer in its float formatter (the round-2 bench segfault)."""
+    G = (_cabi.Game * 1)()
+    P = (_cabi.Ply * 1)()
+    G[0].n_plies = 1; G[0].black_z = -1
+    P[0].own, P[0].enemy, P[0].player, P[0].recorded = 0x0000000810000000, 0x0000001008000000, 1, 1
+    path = str(tmp_path / "play_nan.json")
+    assert E.write_play_data(path, G, 1, P, True, 4) == 8
+    with np.errstate(invalid="ignore", divide="ignore"):
+        pol = list(np.zeros(64) / np.zeros(64).sum())
+    want = json.dumps([[[int(ob.dihedral(P[0].own, t)), int(ob.dihedral(P[0].enemy, t))], pol, -1] for t in range(8)])
+    assert open(path).read() == want and "NaN" in want
