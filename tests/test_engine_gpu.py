@@ -122,6 +122,57 @@ def test_noise_statistics(golden_dir):
     eng.close()
 
 
+def test_k8_positions_vs_reference(golden_dir):
+    """K = 8 + Dirichlet noise on 12 roots from the opening to the endgame against the UNMODIFIED ReversiPlayer
+    (tests/golden/mcts_k8.json, agent/player.py:189-215, 100 repetitions each): mean root visit fractions, mean Q of the most
+    visited move and mean network evaluations per search of 64 independent engine slots."""
+    ref = json.load(open(os.path.join(golden_dir, "mcts_k8.json")))["positions"]
+    assert len(ref) >= 10
+    slots = 64
+    for p in ref:
+        pp = params(simulation_num_per_move=p["sims"], noise_eps=0.25, c_puct=p["c_puct"], change_tau_turn=0)
+        eng = make_engine(pp, games=slots, seed=17)
+        acc, q_top = np.zeros(64), 0.0
+        for slot in range(slots):   # every call searches all slots again with the same per-slot streams; read a different slot each time
+            n, w = eng.search_root(p["own"], p["enemy"], 1, slot)
+            acc += n / n.sum()
+            a = int(np.argmax(n))
+            q_top += float(w[a]) / (float(n[a]) + 1e-5)
+            if slot == 0:
+                exps = eng.stats()["expansions"] / slots
+        reps = slots
+        mine, theirs = acc / reps, np.array(p["mean_visit_frac"])
+        assert set(np.nonzero(mine)[0]) == set(np.nonzero(theirs)[0]), p["turn"]
+        assert np.abs(mine - theirs).max() < 0.04, (p["turn"], np.abs(mine - theirs).max())
+        assert abs(q_top / reps - p["mean_q_of_most_visited"]) < 0.06, (p["turn"], q_top / reps, p["mean_q_of_most_visited"])
+        assert abs(exps - p["mean_expansions"]) <= 0.03 * p["mean_expansions"] + 0.5, (p["turn"], exps, p["mean_expansions"])
+        eng.close()
+
+
+def test_k8_whole_game_distributions_vs_reference(golden_dir):
+    """whole games at K = 8 (50 simulations per move, tau turn 4, noise 0.25) against 80 games of the unmodified reference
+    loop: plies per game, network evaluations per game (the quantity games/s is derived from), final disc difference."""
+    ref = json.load(open(os.path.join(golden_dir, "mcts_k8.json")))["games"]
+    g = ref["games"]
+    pp = params(simulation_num_per_move=ref["sims"], noise_eps=ref["noise_eps"], change_tau_turn=ref["change_tau_turn"], c_puct=ref["c_puct"])
+    n = 512
+    eng = make_engine(pp, games=n, seed=23, max_games=n)
+    eng.run(finished_target=n)
+    mine = eng.poll()
+    eng.close()
+    assert len(mine) == n
+    for x in mine[:16]:
+        replay_check(x)
+    pl, ex = np.array([len(x["plies"]) for x in mine]), np.array([x["expansions"] for x in mine])
+    dd = np.array([bin(x["black"]).count("1") - bin(x["white"]).count("1") for x in mine])
+    r_pl, r_ex, r_dd = (np.array([x[k] for x in g]) for k in ("plies", "expansions", "disc_diff"))
+    se = lambda a, b: np.sqrt(a.var() / a.size + b.var() / b.size)
+    assert abs(pl.mean() - r_pl.mean()) < 4 * se(pl, r_pl) + 0.3, (pl.mean(), r_pl.mean())
+    assert abs(ex.mean() - r_ex.mean()) < 4 * se(ex, r_ex), (ex.mean(), r_ex.mean())
+    assert abs(dd.mean() - r_dd.mean()) < 4 * se(dd, r_dd), (dd.mean(), r_dd.mean())
+    assert 0.7 < dd.std() / r_dd.std() < 1.4
+
+
 def test_search_with_real_network_matches_oracle():
     """Integration of the pieces the deterministic evaluator cannot exercise: the dihedral transform of the leaf
     batch (K3), the network, and the inverse-dihedral policy gather + re-normalisation at expansion.  mini.yml-sized
