@@ -110,6 +110,11 @@ typedef struct rz_net_cfg {
 #define RZ_NET_IMPL_GENERIC 1 /* CUDA-core fp32 kernel, any configuration */
 #define RZ_NET_IMPL_TCGEN05 2 /* fused persistent tcgen05 tower (filters must be 256) */
 
+/* Which kernel serves RZ_NET_IMPL_TCGEN05 from now on (process-wide): 1 = one CTA per tile (csrc/rz_net_tc.cu),
+ * 2 = CTA pairs, cta_group::2, epilogue overlapped with the MMA stream (csrc/rz_net_tc2.cu).  The default comes from
+ * the environment variable RZ_TOWER_KERNEL when the first network call is made.  Used by the tests and benchmarks to
+ * run both on the same inputs. */
+int rz_net_set_tower_kernel(int version);
 int rz_net_create(const rz_net_cfg* cfg, int device, rz_net** out);
 int rz_net_destroy(rz_net* net);
 /* number of float32 values in the weight blob for this configuration.  Blob layout (Keras tensor

@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
                     const uint32_t out = h ? out1 : out0;
                     // 2 chunks of 32 accumulator columns per thread; the TMEM load of the second is in flight while the first
                     // is processed
-                    uint32_t va[32], vb[32], ra[32], rb[32];
+                    uint32_t va[32], vb[32], rr[32];
                     auto prefetch = [&](int c2, uint32_t (&v)[32], uint32_t (&r)[32]) {
                         const int c0 = h * 128 + sub * 64 + c2 * 32;
                         tmem_ld32(tmem + lane_sel + c0, v);
@@ -364,12 +364,12 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
                             }
                         }
                     };
-                    prefetch(0, va, ra);
-                    prefetch(1, vb, rb);
-                    tmem_wait_ld_dep(va); tmem_dep(vb);
-                    if (is_conv2) { tmem_dep(ra); tmem_dep(rb); }
-                    math(0, va, ra); store(0, va);
-                    math(1, vb, rb); store(1, vb);
+                    // the residual buffer rr is consumed by math(0) before prefetch(1) refills it
+                    prefetch(0, va, rr);
+                    tmem_wait_ld_dep(va); if (is_conv2) tmem_dep(rr);
+                    math(0, va, rr); prefetch(1, vb, rr); store(0, va);
+                    tmem_wait_ld_dep(vb); if (is_conv2) tmem_dep(rr);
+                    math(1, vb, rr); store(1, vb);
                     if (!last) {
                         if (keep_res) tmem_wait_st();
                         fence_proxy_async();
