@@ -90,6 +90,10 @@ typedef struct rz_env_state {
 uint64_t rz_find_correct_moves_host(uint64_t own, uint64_t enemy);
 uint64_t rz_calc_flip_host(int pos, uint64_t own, uint64_t enemy);
 uint64_t rz_dihedral_host(uint64_t x, int t);
+/* Host twin of the BIT-SLICED formulation the batched GPU operators use (csrc/rz_bitsliced.cuh: 32 positions per thread,
+ * one register per square): pos == NULL: out[i] = find_correct_moves(own[i], enemy[i]); else out[i] = calc_flip(pos[i], ..).
+ * Same header compiled for the host; exists so that the formulation can be held against the oracle without a GPU. */
+int rz_bitsliced_host(const uint8_t* pos, const uint64_t* own, const uint64_t* enemy, uint64_t* out, size_t n);
 void rz_env_reset_host(rz_env_state* s);                                              /* reversi_env.py:26-32 */
 void rz_env_update_host(rz_env_state* s, uint64_t black, uint64_t white, int next_player); /* :34-40 */
 void rz_env_step_host(rz_env_state* s, int action /* -1 = None */);                   /* :42-74 */

@@ -2,11 +2,18 @@
 //
 // HBM-bound integer work: 24 B / position for the legal-move mask, 25 B for the flip
 // mask, 42+ B for the fused step.  Layout is structure-of-arrays so every warp access is a fully
-// coalesced run; each thread handles two consecutive positions through 128-bit loads/stores, inputs
-// are streamed with ld.global.nc.L1::no_allocate, outputs with st.global.cs.  Grids are a multiple of
-// the SM count (persistent grid-stride loop).
+// coalesced run.  Two formulations:
+//   * bit-sliced (rz_bitsliced.cuh; default for the legal-move and flip operators from 1024 positions on): one thread owns 32
+//     positions transposed into one register per square, ~67 integer instructions per position, one CTA of 256 threads per SM
+//     (231-240 registers), a warp walks tiles of 1024 positions with 256-byte contiguous loads / stores;
+//   * scalar (rz_bitboard.cuh; the tail of a batch, small batches, RZ_K1_IMPL=scalar): two consecutive positions per thread
+//     through 128-bit loads / stores, ~180 instructions per position -- integer-issue-bound at a third of the HBM roofline.
+// Inputs are streamed with ld.global.nc.L1::no_allocate, outputs with st.global.cs.  Grids are a multiple of the SM count
+// (persistent grid-stride loops).
 #include <stdlib.h>
+#include <string.h>
 #include "rz_bitboard.cuh"
+#include "rz_bitsliced.cuh"
 #include "rz_common.cuh"
 
 namespace rz {
@@ -26,6 +33,56 @@ __device__ __forceinline__ void stg_stream_u64x2(u64* p, u64 a, u64 b) {
 }
 
 constexpr int kThreads = 256;
+
+__device__ __forceinline__ void stg_stream_u64(u64* p, u64 a) { asm volatile("st.global.cs.u64 [%0], %1;" ::"l"(p), "l"(a) : "memory"); }
+
+// bit-sliced operators: warp w of the grid handles tiles w, w + n_warps, ...; thread t of the warp owns the 32 positions
+// tile * 1024 + i * 32 + t (i = 0..31), so load / store instruction i of the warp covers 256 contiguous bytes
+__global__ void __launch_bounds__(kThreads, 1) k1_find_correct_moves_bs(const u64* __restrict__ own, const u64* __restrict__ enemy,
+                                                                        u64* __restrict__ out, size_t n_tiles) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t t = warp; t < n_tiles; t += n_warps) {
+        const size_t base = t * 1024 + lane;
+        u64 o[32], e[32], m[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { o[i] = ldg_stream_u64(own + base + i * 32); e[i] = ldg_stream_u64(enemy + base + i * 32); }
+        bs::find_correct_moves32(o, e, m);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) stg_stream_u64(out + base + i * 32, m[i]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k1_calc_flip_bs(const uint8_t* __restrict__ pos, const u64* __restrict__ own,
+                                                               const u64* __restrict__ enemy, u64* __restrict__ out, size_t n_tiles) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t t = warp; t < n_tiles; t += n_warps) {
+        const size_t base = t * 1024 + lane;
+        u64 o[32], e[32], f[32];
+        uint8_t ps[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            o[i] = ldg_stream_u64(own + base + i * 32); e[i] = ldg_stream_u64(enemy + base + i * 32);
+            ps[i] = __ldg(pos + base + i * 32);
+        }
+        bs::calc_flip32(ps, o, e, f);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) stg_stream_u64(out + base + i * 32, f[i]);
+    }
+}
+
+static bool k1_use_bitsliced() {
+    static int v = -1;
+    if (v < 0) { const char* s = getenv("RZ_K1_IMPL"); v = (s && strcmp(s, "scalar") == 0) ? 0 : 1; }
+    return v == 1;
+}
+static int grid_for_tiles(size_t tiles) {
+    const size_t per_cta = kThreads / 32;
+    size_t blocks = (tiles + per_cta - 1) / per_cta;
+    if (blocks > (size_t)num_sms()) blocks = (size_t)num_sms();   // one CTA of 256 threads x ~240 registers per SM
+    return (int)(blocks < 1 ? 1 : blocks);
+}
 
 __global__ void __launch_bounds__(kThreads) k1_find_correct_moves(const u64* __restrict__ own, const u64* __restrict__ enemy,
                                                                   u64* __restrict__ out, size_t n, int vec_ok) {
@@ -114,6 +171,13 @@ extern "C" {
 int rz_find_correct_moves_dev(const uint64_t* own, const uint64_t* enemy, uint64_t* out, size_t n, void* stream) {
     RZ_REQUIRE(n == 0 || (own && enemy && out), "rz_find_correct_moves_dev: null pointer");
     if (n == 0) return RZ_OK;
+    if (k1_use_bitsliced() && n >= 1024) {  // whole tiles of 1024 positions bit-sliced, the rest below
+        const size_t tiles = n / 1024;
+        k1_find_correct_moves_bs<<<grid_for_tiles(tiles), kThreads, 0, (cudaStream_t)stream>>>(own, enemy, out, tiles);
+        RZ_LAUNCH_CHECK();
+        own += tiles * 1024; enemy += tiles * 1024; out += tiles * 1024; n -= tiles * 1024;
+        if (n == 0) return RZ_OK;
+    }
     const int vec = aligned16(own) && aligned16(enemy) && aligned16(out);
     k1_find_correct_moves<<<grid_for(vec ? (n + 1) / 2 : n), kThreads, 0, (cudaStream_t)stream>>>(own, enemy, out, n, vec);
     RZ_LAUNCH_CHECK();
@@ -123,6 +187,13 @@ int rz_find_correct_moves_dev(const uint64_t* own, const uint64_t* enemy, uint64
 int rz_calc_flip_dev(const uint8_t* pos, const uint64_t* own, const uint64_t* enemy, uint64_t* out, size_t n, void* stream) {
     RZ_REQUIRE(n == 0 || (pos && own && enemy && out), "rz_calc_flip_dev: null pointer");
     if (n == 0) return RZ_OK;
+    if (k1_use_bitsliced() && n >= 1024) {
+        const size_t tiles = n / 1024;
+        k1_calc_flip_bs<<<grid_for_tiles(tiles), kThreads, 0, (cudaStream_t)stream>>>(pos, own, enemy, out, tiles);
+        RZ_LAUNCH_CHECK();
+        pos += tiles * 1024; own += tiles * 1024; enemy += tiles * 1024; out += tiles * 1024; n -= tiles * 1024;
+        if (n == 0) return RZ_OK;
+    }
     const int vec = aligned16(own) && aligned16(enemy) && aligned16(out) && ((reinterpret_cast<uintptr_t>(pos) & 1) == 0);
     k1_calc_flip<<<grid_for(vec ? (n + 1) / 2 : n), kThreads, 0, (cudaStream_t)stream>>>(pos, own, enemy, out, n, vec);
     RZ_LAUNCH_CHECK();
@@ -208,6 +279,23 @@ int rz_step(uint64_t* black, uint64_t* white, uint8_t* next_player, uint8_t* tur
 // ---- scalar host twins (single-environment Python objects) ---------------------------------------
 uint64_t rz_find_correct_moves_host(uint64_t own, uint64_t enemy) { return find_correct_moves(own, enemy); }
 uint64_t rz_calc_flip_host(int pos, uint64_t own, uint64_t enemy) { return calc_flip(pos & 63, own, enemy); }
+
+// host twins of the bit-sliced operators (the same header compiled for the host, groups of 32 consecutive positions): they let
+// the CPU test suite hold the formulation the GPU kernels use against the oracle.  pos may be NULL for the legal-move variant.
+int rz_bitsliced_host(const uint8_t* pos, const uint64_t* own, const uint64_t* enemy, uint64_t* out, size_t n) {
+    RZ_REQUIRE(n == 0 || (own && enemy && out), "rz_bitsliced_host: null pointer");
+    for (size_t at = 0; at < n; at += 32) {
+        u64 o[32], e[32], r[32];
+        uint8_t ps[32];
+        const size_t m = n - at < 32 ? n - at : 32;
+        for (size_t i = 0; i < 32; ++i) {
+            o[i] = i < m ? own[at + i] : 0; e[i] = i < m ? enemy[at + i] : 0; ps[i] = (pos && i < m) ? pos[at + i] : 0;
+        }
+        if (pos) bs::calc_flip32(ps, o, e, r); else bs::find_correct_moves32(o, e, r);
+        for (size_t i = 0; i < m; ++i) out[at + i] = r[i];
+    }
+    return RZ_OK;
+}
 uint64_t rz_dihedral_host(uint64_t x, int t) { return dihedral(x, t & 7); }
 void rz_env_reset_host(rz_env_state* s) {
     EnvState e; env_reset(e);

@@ -76,32 +76,14 @@ __device__ __forceinline__ void umma2_commit(uint32_t bar) {
                  "h"((uint16_t)3)
                  : "memory");
 }
-// arrive on the barrier at the same offset in CTA `rank` of the cluster (release at cluster scope: the arriving thread's
-// shared-memory / TMEM accesses are ordered before the waiter's)
+// arrive on the barrier at the same offset in CTA `rank` of the cluster.  Plain (default-semantics) arrive and wait, as the
+// 2-SM GEMM pipelines use them: a first version with .release.cluster arrives and .acquire.cluster waits was correct but
+// spent ~0.5 us per weight stage in the MMA thread's cluster-scope acquire (100 ms per launch instead of 36).
 __device__ __forceinline__ void mbar_arrive_cta(uint32_t bar, uint32_t rank) {
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(rank));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquire at cluster scope (remote arrivals)
-    uint32_t ok = 0;
-    long long t0 = 0;
-    for (uint32_t spin = 0; !ok; ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (!ok && (spin & 1023) == 1023) {
-            const long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 8000000000LL) __trap();
-        }
-    }
-}
-
 __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Params pp) {
     Params p = pp;
     if (p.n_dev) p.n = *p.n_dev;
@@ -172,10 +154,10 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
             bool first = true;
             for (uint32_t it = 0; it < iters; ++it) {
                 // layer 0: [128 rows x 32] im2col tile per CTA x [32 x 128] per output half
-                mbar_wait_cluster(bar_a0, a0_par);
+                mbar_wait(bar_a0, a0_par);
                 a0_par ^= 1;
                 tc_fence_after();
-                if (first) { mbar_wait_cluster(bar_w0, 0); first = false; }
+                if (first) { mbar_wait(bar_w0, 0); first = false; }
 #pragma unroll
                 for (uint32_t nh = 0; nh < 2; ++nh) {
 #pragma unroll
@@ -190,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
                     for (uint32_t nh = 0; nh < 2; ++nh) {
                         for (uint32_t kh = 0; kh < 2; ++kh) {
                             if (nh == 0) {  // written by the previous layer's half-kh epilogue of BOTH CTAs (which also drained acc[kh])
-                                mbar_wait_cluster(bar_x(kh), x_par[kh]);
+                                mbar_wait(bar_x(kh), x_par[kh]);
                                 x_par[kh] ^= 1;
                                 tc_fence_after();
                             }
@@ -199,7 +181,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
                                 // tap (kh, kw) reads input pixel (y + kh - 1, x + kw - 1): slot offset 2*kh, chunk offset kw
                                 const uint32_t a_tap = xb + (2 * (tap / 3)) * kActSlot + (tap % 3) * 16;
                                 for (uint32_t kbl = 0; kbl < 2; ++kbl) {
-                                    mbar_wait_cluster(bar_full(stage), phase);
+                                    mbar_wait(bar_full(stage), phase);
                                     tc_fence_after();
                                     const uint32_t b_st = base + kOffW + stage * kStageBytes;
 #pragma unroll
@@ -295,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
                 const uint32_t out1 = base + kOffAct + kHalfBytes + row_off;
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
-                    mbar_wait_cluster(bar_acc(h), acc_par[h]);
+                    mbar_wait(bar_acc(h), acc_par[h]);
                     acc_par[h] ^= 1;
                     tc_fence_after();
                     const uint32_t out = h ? out1 : out0;

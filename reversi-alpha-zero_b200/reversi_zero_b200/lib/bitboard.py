@@ -101,6 +101,18 @@ def calc_flip_batch(pos, own, enemy):
     return out
 
 
+def bitsliced_host(own, enemy, pos=None):
+    """Host twin of the bit-sliced formulation the batched GPU operators use (rz_bitsliced_host): legal-move masks when
+    ``pos`` is None, flip masks otherwise.  For tests; the product path is the GPU."""
+    own, enemy = _u64(own), _u64(enemy)
+    out = np.empty_like(own)
+    p = None if pos is None else np.ascontiguousarray(pos, dtype=np.uint8)
+    _cabi.check(_cabi.lib().rz_bitsliced_host(None if p is None else p.ctypes.data_as(_cabi.u8p), own.ctypes.data_as(_cabi.u64p),
+                                              enemy.ctypes.data_as(_cabi.u64p), out.ctypes.data_as(_cabi.u64p), own.size),
+                "rz_bitsliced_host")
+    return out
+
+
 def dihedral_batch(x, t, device="cuda:0"):
     """rz_dihedral_dev over arrays: out[i] = flip_vertical if t[i] & 4, then (t[i] & 3) x rotate90 of x[i]
     (lib/bitboard.py:119-159 in the order of agent/player.py:166-179,300-305) -- the device code the engine's leaf

@@ -72,3 +72,26 @@ def test_env_mirror_vs_golden(golden_dir):
     env = ReversiEnv().reset()
     assert env.get_own_and_enemy() == (env.board.black, env.board.white) and env.observation is env.board
     assert Winner.draw.value == 3 and Player.white.value == 2
+
+
+def test_bitsliced_formulation_matches_oracle_and_goldens(golden_dir):
+    """csrc/rz_bitsliced.cuh (32 positions per thread, one register per square -- what the batched GPU kernels run) compiled
+    for the host: legal-move and flip masks bit-identical to the reference's golden vectors (lib/bitboard.py:53-116, all 64
+    `pos` including illegal ones) and to the C oracle on the config-5 recipe, ragged sizes included."""
+    import numpy as np
+    from oracle import bitboard as ob
+    from reversi_zero_b200.lib import bitboard as zb
+    g = np.load(os.path.join(golden_dir, "bitboard.npz"))
+    assert np.array_equal(zb.bitsliced_host(g["own"], g["enemy"]), g["legal"])
+    assert np.array_equal(zb.bitsliced_host(g["own"], g["enemy"], g["pos"]), g["flip"])
+    for row, i in zip(g["flip_all"], g["sub"]):
+        assert np.array_equal(zb.bitsliced_host(np.full(64, g["own"][i]), np.full(64, g["enemy"][i]), np.arange(64, dtype=np.uint8)), row)
+    rng = np.random.default_rng(20260922)
+    for n in (0, 1, 31, 32, 33, 1000, 200_003):
+        a, b, r = (rng.integers(0, 2 ** 64, size=n, dtype=np.uint64) for _ in range(3))
+        occ = a.copy()
+        occ[: n // 3] &= b[: n // 3]
+        occ[2 * (n // 3):] |= b[2 * (n // 3):]
+        own, enemy, pos = occ & r, occ & ~r, rng.integers(0, 64, size=n, dtype=np.uint8)
+        assert np.array_equal(zb.bitsliced_host(own, enemy), ob.find_correct_moves_batch(own, enemy))
+        assert np.array_equal(zb.bitsliced_host(own, enemy, pos), ob.calc_flip_batch(pos, own, enemy))

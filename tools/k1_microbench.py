@@ -77,4 +77,15 @@ def run(n=10_000_000, iters=100, warmup=5):
 
 
 if __name__ == "__main__":
-    print(json.dumps(run()))
+    # the default formulation (bit-sliced) in this process; the scalar one (RZ_K1_IMPL is read once per process) in a child
+    res = run()
+    res["impl"] = os.environ.get("RZ_K1_IMPL", "bitsliced")
+    if "--both" in sys.argv and res["impl"] != "scalar":
+        import subprocess
+        out = subprocess.run([sys.executable, os.path.abspath(__file__)], env=dict(os.environ, RZ_K1_IMPL="scalar"), capture_output=True, text=True)
+        try:
+            sc = json.loads(out.stdout.strip().splitlines()[-1])
+            res["scalar_formulation"] = {k: sc[k] for k in ("find_correct_moves", "calc_flip")}
+        except Exception as ex:
+            res["scalar_formulation"] = dict(error=str(ex), stderr=out.stderr[-500:])
+    print(json.dumps(res))
