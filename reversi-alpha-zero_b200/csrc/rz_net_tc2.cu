@@ -84,6 +84,10 @@ __device__ __forceinline__ void mbar_arrive_cta(uint32_t bar, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(rank));
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
+// EXP != 0 are MEASUREMENT variants (RZ_TOWER_EXPERIMENT; results are garbage): 1 = the epilogue keeps only the barrier
+// protocol (time of the MMA stream + weight pipeline alone); 3 = no weight pipeline either (the MMA thread neither waits for
+// stages nor frees them, producer and relay idle: the bare issue rate of the MMA stream over whatever is in shared memory).
+template <int EXP>
 __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Params pp) {
     Params p = pp;
     if (p.n_dev) p.n = *p.n_dev;
@@ -135,7 +139,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
             mbar_expect_tx(bar_w0, kW0Bytes);
             bulk_g2s(base + kOffW0, reinterpret_cast<const uint8_t*>(p.w0) + crank * kW0Bytes, kW0Bytes, bar_w0);
             uint32_t stage = 0, phase = 0;
-            for (uint32_t it = 0; it < iters; ++it) {
+            for (uint32_t it = 0; it < (EXP == 3 ? 0u : iters); ++it) {
                 for (int l = 1; l < L; ++l) {
                     const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w) + ((size_t)(l - 1) * kStagesPerLayer * 2 + crank) * kStageBytes;
                     for (uint32_t s = 0; s < kStagesPerLayer; ++s) {
@@ -181,14 +185,16 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
                                 // tap (kh, kw) reads input pixel (y + kh - 1, x + kw - 1): slot offset 2*kh, chunk offset kw
                                 const uint32_t a_tap = xb + (2 * (tap / 3)) * kActSlot + (tap % 3) * 16;
                                 for (uint32_t kbl = 0; kbl < 2; ++kbl) {
-                                    mbar_wait(bar_full(stage), phase);
-                                    tc_fence_after();
+                                    if (EXP != 3) {
+                                        mbar_wait(bar_full(stage), phase);
+                                        tc_fence_after();
+                                    }
                                     const uint32_t b_st = base + kOffW + stage * kStageBytes;
 #pragma unroll
                                     for (uint32_t j = 0; j < 4; ++j)
                                         umma2_f16(tmem + nh * 128, smem_desc(a_tap + (kbl * 8 + 2 * j) * kActCg, kActCg, kActSlot),
                                                   smem_desc(b_st + 2 * j * 1024, 1024, 128), kIdesc, (kh | tap | kbl | j) != 0);
-                                    umma2_commit(bar_empty(stage));
+                                    if (EXP != 3) umma2_commit(bar_empty(stage));
                                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                                 }
                             }
@@ -202,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
             uint32_t stage = 0, phase = 0;
             mbar_wait(bar_w0, 0);
             mbar_arrive_cta(bar_w0, 0);
-            for (uint32_t it = 0; it < iters; ++it)
+            for (uint32_t it = 0; it < (EXP == 3 ? 0u : iters); ++it)
                 for (int l = 1; l < L; ++l)
                     for (uint32_t s = 0; s < kStagesPerLayer; ++s) {
                         mbar_wait(bar_full(stage), phase);
@@ -280,6 +286,10 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
                     mbar_wait(bar_acc(h), acc_par[h]);
                     acc_par[h] ^= 1;
                     tc_fence_after();
+                    if (EXP != 0) {
+                        if (!last) { tc_fence_before(); mbar_arrive_cta(bar_x(h), 0); }
+                        continue;
+                    }
                     const uint32_t out = h ? out1 : out0;
                     // 2 chunks of 32 accumulator columns per thread; the TMEM load of the second is in flight while the first
                     // is processed
@@ -472,10 +482,13 @@ int net_forward_tc2(rz_net* net, const uint64_t* own, const uint64_t* enemy, flo
     RZ_REQUIRE(net->cfg.filters == 256, "tcgen05 tower requires 256 filters");
     RZ_REQUIRE(net->cfg.value_fc <= (int)tc2::kMaxV, "tcgen05 tower supports value_fc_size <= %u", tc2::kMaxV);
     RZ_REQUIRE(n < (1ull << 31), "batch too large");
-    static bool attr_set = false;
-    if (!attr_set) {
-        RZ_CUDA_TRY(cudaFuncSetAttribute(tc2::net_tower_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2::kSmemAlloc));
-        attr_set = true;
+    static int experiment = -1;
+    if (experiment < 0) {
+        RZ_CUDA_TRY(cudaFuncSetAttribute(tc2::net_tower_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2::kSmemAlloc));
+        RZ_CUDA_TRY(cudaFuncSetAttribute(tc2::net_tower_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2::kSmemAlloc));
+        RZ_CUDA_TRY(cudaFuncSetAttribute(tc2::net_tower_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2::kSmemAlloc));
+        const char* ex = getenv("RZ_TOWER_EXPERIMENT");
+        experiment = ex ? atoi(ex) : 0;
     }
     tc::Params p;
     p.w0 = net->tc2_w0; p.w = net->tc2_w; p.ss = net->scale_shift; p.blob = net->blob;
@@ -495,7 +508,9 @@ int net_forward_tc2(rz_net* net, const uint64_t* own, const uint64_t* enemy, flo
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    RZ_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc2::net_tower_pair_kernel, p));
+    if (experiment == 1) RZ_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc2::net_tower_pair_kernel<1>, p));
+    else if (experiment == 3) RZ_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc2::net_tower_pair_kernel<3>, p));
+    else RZ_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc2::net_tower_pair_kernel<0>, p));
     RZ_LAUNCH_CHECK();
     return RZ_OK;
 }
