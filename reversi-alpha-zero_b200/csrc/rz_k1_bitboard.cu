@@ -14,6 +14,7 @@
 #include <string.h>
 #include "rz_bitboard.cuh"
 #include "rz_bitsliced.cuh"
+#include "rz_tc_common.cuh"   // mbarrier / bulk-copy wrappers
 #include "rz_common.cuh"
 
 namespace rz {
@@ -72,10 +73,79 @@ __global__ void __launch_bounds__(kThreads, 1) k1_calc_flip_bs(const uint8_t* __
     }
 }
 
-static bool k1_use_bitsliced() {
+// The same operators with the inputs staged through shared memory: a tile of 1024 positions is 8 KB contiguous in each
+// input array, so one lane fetches it with one cp.async.bulk per array (completion on the warp's own mbarrier); as soon as the
+// warp has moved a tile from shared memory into registers it starts the copy of its NEXT tile, which lands while the ~2100
+// logic instructions of the current one execute.  The register-only kernels above cannot overlap the two phases (their 231-255
+// registers leave two warps per scheduler and no room for a second set of inputs) and stop at ~0.5 of the HBM roofline.
+constexpr uint32_t kStagePerWarp = 2 * 8192 + 1024;   // own, enemy, pos
+constexpr uint32_t kStagedSmem = (kThreads / 32) * kStagePerWarp + 64 + 128;
+
+template <bool FLIP>
+__global__ void __launch_bounds__(kThreads, 1) k1_bs_staged(const uint8_t* __restrict__ pos, const u64* __restrict__ own,
+                                                            const u64* __restrict__ enemy, u64* __restrict__ out, size_t n_tiles) {
+    extern __shared__ uint8_t k1_smem_raw[];
+    const uint32_t base = (tc::smem_u32(k1_smem_raw) + 127u) & ~127u;
+    uint8_t* sm = k1_smem_raw + (base - tc::smem_u32(k1_smem_raw));
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t bar = base + (kThreads / 32) * kStagePerWarp + w * 8;
+    const uint32_t s_own = base + w * kStagePerWarp, s_en = s_own + 8192, s_pos = s_own + 16384;
+    const u64* so = reinterpret_cast<const u64*>(sm + w * kStagePerWarp);
+    const u64* se = so + 1024;
+    const uint8_t* sp = sm + w * kStagePerWarp + 16384;
+    if (lane == 0) {
+        tc::mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto fetch = [&](size_t t) {   // lane 0 only
+        tc::mbar_expect_tx(bar, FLIP ? 16384u + 1024u : 16384u);
+        tc::bulk_g2s(s_own, own + t * 1024, 8192, bar);
+        tc::bulk_g2s(s_en, enemy + t * 1024, 8192, bar);
+        if (FLIP) tc::bulk_g2s(s_pos, pos + t * 1024, 1024, bar);
+    };
+    uint32_t phase = 0;
+    if (warp < n_tiles && lane == 0) fetch(warp);
+    for (size_t t = warp; t < n_tiles; t += n_warps) {
+        u64 o[32], e[32], r[32];
+        uint8_t ps[32];
+        tc::mbar_wait(bar, phase);
+        phase ^= 1;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            o[i] = so[i * 32 + lane]; e[i] = se[i * 32 + lane];
+            if (FLIP) ps[i] = sp[i * 32 + lane];
+        }
+        __syncwarp();                       // every lane has its copy: the staging buffer may be refilled
+        if (lane == 0 && t + n_warps < n_tiles) {
+            tc::fence_proxy_async();
+            fetch(t + n_warps);
+        }
+        if (FLIP) bs::calc_flip32(ps, o, e, r); else bs::find_correct_moves32(o, e, r);
+        const size_t ob = t * 1024 + lane;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) stg_stream_u64(out + ob + i * 32, r[i]);
+    }
+}
+
+// RZ_K1_IMPL: "scalar", "bitsliced" (register-only), "staged" (bit-sliced + shared-memory staging); default per operator below
+static int k1_impl() {
     static int v = -1;
-    if (v < 0) { const char* s = getenv("RZ_K1_IMPL"); v = (s && strcmp(s, "scalar") == 0) ? 0 : 1; }
-    return v == 1;
+    if (v < 0) {
+        const char* s = getenv("RZ_K1_IMPL");
+        v = !s ? 3 : (strcmp(s, "scalar") == 0 ? 0 : (strcmp(s, "bitsliced") == 0 ? 1 : (strcmp(s, "staged") == 0 ? 2 : 3)));
+    }
+    return v;
+}
+static int k1_staged_attr() {
+    static bool done = false;
+    if (!done) {
+        RZ_CUDA_TRY(cudaFuncSetAttribute(k1_bs_staged<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedSmem));
+        RZ_CUDA_TRY(cudaFuncSetAttribute(k1_bs_staged<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedSmem));
+        done = true;
+    }
+    return RZ_OK;
 }
 static int grid_for_tiles(size_t tiles) {
     const size_t per_cta = kThreads / 32;
@@ -171,9 +241,15 @@ extern "C" {
 int rz_find_correct_moves_dev(const uint64_t* own, const uint64_t* enemy, uint64_t* out, size_t n, void* stream) {
     RZ_REQUIRE(n == 0 || (own && enemy && out), "rz_find_correct_moves_dev: null pointer");
     if (n == 0) return RZ_OK;
-    if (k1_use_bitsliced() && n >= 1024) {  // whole tiles of 1024 positions bit-sliced, the rest below
+    const int impl = k1_impl() == 3 ? 2 : k1_impl();   // default: bit-sliced with staging
+    if (impl != 0 && n >= 1024) {  // whole tiles of 1024 positions bit-sliced, the rest below
         const size_t tiles = n / 1024;
-        k1_find_correct_moves_bs<<<grid_for_tiles(tiles), kThreads, 0, (cudaStream_t)stream>>>(own, enemy, out, tiles);
+        if (impl == 2 && aligned16(own) && aligned16(enemy)) {
+            RZ_TRY(k1_staged_attr());
+            k1_bs_staged<false><<<grid_for_tiles(tiles), kThreads, kStagedSmem, (cudaStream_t)stream>>>(nullptr, own, enemy, out, tiles);
+        } else {
+            k1_find_correct_moves_bs<<<grid_for_tiles(tiles), kThreads, 0, (cudaStream_t)stream>>>(own, enemy, out, tiles);
+        }
         RZ_LAUNCH_CHECK();
         own += tiles * 1024; enemy += tiles * 1024; out += tiles * 1024; n -= tiles * 1024;
         if (n == 0) return RZ_OK;
@@ -187,9 +263,15 @@ int rz_find_correct_moves_dev(const uint64_t* own, const uint64_t* enemy, uint64
 int rz_calc_flip_dev(const uint8_t* pos, const uint64_t* own, const uint64_t* enemy, uint64_t* out, size_t n, void* stream) {
     RZ_REQUIRE(n == 0 || (pos && own && enemy && out), "rz_calc_flip_dev: null pointer");
     if (n == 0) return RZ_OK;
-    if (k1_use_bitsliced() && n >= 1024) {
+    const int impl = k1_impl() == 3 ? 2 : k1_impl();
+    if (impl != 0 && n >= 1024) {
         const size_t tiles = n / 1024;
-        k1_calc_flip_bs<<<grid_for_tiles(tiles), kThreads, 0, (cudaStream_t)stream>>>(pos, own, enemy, out, tiles);
+        if (impl == 2 && aligned16(own) && aligned16(enemy) && aligned16(pos)) {
+            RZ_TRY(k1_staged_attr());
+            k1_bs_staged<true><<<grid_for_tiles(tiles), kThreads, kStagedSmem, (cudaStream_t)stream>>>(pos, own, enemy, out, tiles);
+        } else {
+            k1_calc_flip_bs<<<grid_for_tiles(tiles), kThreads, 0, (cudaStream_t)stream>>>(pos, own, enemy, out, tiles);
+        }
         RZ_LAUNCH_CHECK();
         pos += tiles * 1024; own += tiles * 1024; enemy += tiles * 1024; out += tiles * 1024; n -= tiles * 1024;
         if (n == 0) return RZ_OK;

@@ -38,12 +38,12 @@ constexpr int kThreads = 320;  // warp 0 weight producer, warp 1 MMA issuer (lea
 constexpr int kEpiThreads = 256;
 constexpr uint32_t kActCg = 2896, kActSlot = 144;
 constexpr uint32_t kHalfBytes = 16 * kActCg;  // 46,336: 128 channels of the operand
-constexpr uint32_t kStageBytes = 8192, kStages = 6;   // per CTA: one tap x 64 input channels x 64 of the 128 output channels
+constexpr uint32_t kStageBytes = 8192;                // per CTA: one tap x 64 input channels x 64 of the 128 output channels
+constexpr uint32_t kMaxStages = 7;                    // ring depth is a template parameter (6 or 7), the ring sits last
 constexpr uint32_t kStagesPerLayer = 72;              // 2 output halves x 2 input halves x 9 taps x 2 blocks of 64 channels
 constexpr uint32_t kA0Bytes = 8192, kW0Bytes = 8192;
 constexpr uint32_t kOffAct = 0;                       // half-buffers A (0), B (1), C (2)
-constexpr uint32_t kOffW = kOffAct + 3 * kHalfBytes;
-constexpr uint32_t kOffA0 = kOffW + kStages * kStageBytes;
+constexpr uint32_t kOffA0 = kOffAct + 3 * kHalfBytes;
 constexpr uint32_t kOffW0 = kOffA0 + kA0Bytes;
 constexpr uint32_t kOffSS = kOffW0 + kW0Bytes;           // 2 x [scale 256][shift 256] fp32
 constexpr uint32_t kOffPart = kOffSS + 2 * 2048;         // [2 column sub-halves][128 rows][4] fp32 head partial sums
@@ -53,11 +53,11 @@ constexpr uint32_t kOffLogit = kOffHv + 2 * 64 * 4;      // [2][64]
 constexpr uint32_t kMaxV = 512;
 constexpr uint32_t kOffFc1 = kOffLogit + 2 * 64 * 4;     // [2][kMaxV]
 constexpr uint32_t kOffBar = kOffFc1 + 2 * kMaxV * 4;    // mbarriers
-constexpr uint32_t kNumBars = 2 * kStages + 6;           // full, empty, w0, a0, x[2], acc[2]
+constexpr uint32_t kNumBars = 2 * kMaxStages + 6;        // full, empty, w0, a0, x[2], acc[2]
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
-constexpr uint32_t kSmemBytes = kOffTmemPtr + 16;
-constexpr uint32_t kSmemAlloc = kSmemBytes + 128;  // slack for manual 128 B alignment
-static_assert(kSmemAlloc <= 232448, "shared memory budget exceeded");
+constexpr uint32_t kOffW = (kOffTmemPtr + 16 + 127) & ~127u;   // weight ring
+constexpr uint32_t smem_alloc(uint32_t stages) { return kOffW + stages * kStageBytes + 128; }  // + slack for manual 128 B alignment
+static_assert(smem_alloc(kMaxStages) <= 232448, "shared memory budget exceeded");
 
 // instruction descriptor, kind::f16: D = f32, A = B = f16, K-major both, N = 128, M = 256 (cta_group::2)
 constexpr uint32_t kIdesc = (1u << 4) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
@@ -87,8 +87,10 @@ __device__ __forceinline__ void mbar_arrive_cta(uint32_t bar, uint32_t rank) {
 // EXP != 0 are MEASUREMENT variants (RZ_TOWER_EXPERIMENT; results are garbage): 1 = the epilogue keeps only the barrier
 // protocol (time of the MMA stream + weight pipeline alone); 3 = no weight pipeline either (the MMA thread neither waits for
 // stages nor frees them, producer and relay idle: the bare issue rate of the MMA stream over whatever is in shared memory).
-template <int EXP>
+// 4 = the leader does not wait for the peer's "my half has landed" relay (the cost of that hop).
+template <int EXP, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Params pp) {
+    constexpr uint32_t kStages = STAGES;
     Params p = pp;
     if (p.n_dev) p.n = *p.n_dev;
     extern __shared__ uint8_t smem_raw[];
@@ -97,8 +99,8 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = base + kOffBar;
     auto bar_full = [&](uint32_t s) { return bar0 + s * 8; };
-    auto bar_empty = [&](uint32_t s) { return bar0 + (kStages + s) * 8; };
-    const uint32_t bar_w0 = bar0 + 2 * kStages * 8, bar_a0 = bar_w0 + 8;
+    auto bar_empty = [&](uint32_t s) { return bar0 + (kMaxStages + s) * 8; };
+    const uint32_t bar_w0 = bar0 + 2 * kMaxStages * 8, bar_a0 = bar_w0 + 8;
     auto bar_x = [&](uint32_t h) { return bar_w0 + 16 + h * 8; };     // operand half h of the next layer written (both CTAs)
     auto bar_acc = [&](uint32_t h) { return bar_w0 + 32 + h * 8; };   // accumulator half h of the current layer complete
     const uint32_t ntiles = (p.n + 1) >> 1;
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
     fence_proxy_async();
     if (threadIdx.x == 0) {
         // the leader's `full` barriers also collect the peer's "my half of the stage has landed" relay
-        for (uint32_t s = 0; s < kStages; ++s) { mbar_init(bar_full(s), leader ? 2 : 1); mbar_init(bar_empty(s), 1); }
+        for (uint32_t s = 0; s < kStages; ++s) { mbar_init(bar_full(s), (leader && EXP != 4) ? 2 : 1); mbar_init(bar_empty(s), 1); }
         mbar_init(bar_w0, leader ? 2 : 1);
         mbar_init(bar_a0, 2 * kEpiThreads);
         mbar_init(bar_x(0), 2 * kEpiThreads);
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
                 for (int l = 1; l < L; ++l)
                     for (uint32_t s = 0; s < kStagesPerLayer; ++s) {
                         mbar_wait(bar_full(stage), phase);
-                        mbar_arrive_cta(bar_full(stage), 0);
+                        if (EXP != 4) mbar_arrive_cta(bar_full(stage), 0);
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
         }
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
                     mbar_wait(bar_acc(h), acc_par[h]);
                     acc_par[h] ^= 1;
                     tc_fence_after();
-                    if (EXP != 0) {
+                    if (EXP == 1 || EXP == 3) {
                         if (!last) { tc_fence_before(); mbar_arrive_cta(bar_x(h), 0); }
                         continue;
                     }
@@ -482,13 +484,19 @@ int net_forward_tc2(rz_net* net, const uint64_t* own, const uint64_t* enemy, flo
     RZ_REQUIRE(net->cfg.filters == 256, "tcgen05 tower requires 256 filters");
     RZ_REQUIRE(net->cfg.value_fc <= (int)tc2::kMaxV, "tcgen05 tower supports value_fc_size <= %u", tc2::kMaxV);
     RZ_REQUIRE(n < (1ull << 31), "batch too large");
-    static int experiment = -1;
+    static int experiment = -1, stages = 6;
+    typedef void (*kern_t)(const tc::Params);
+    static kern_t kern = nullptr;
     if (experiment < 0) {
-        RZ_CUDA_TRY(cudaFuncSetAttribute(tc2::net_tower_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2::kSmemAlloc));
-        RZ_CUDA_TRY(cudaFuncSetAttribute(tc2::net_tower_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2::kSmemAlloc));
-        RZ_CUDA_TRY(cudaFuncSetAttribute(tc2::net_tower_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2::kSmemAlloc));
         const char* ex = getenv("RZ_TOWER_EXPERIMENT");
+        const char* st = getenv("RZ_TOWER_STAGES");
         experiment = ex ? atoi(ex) : 0;
+        stages = (st && atoi(st) == 7) ? 7 : 6;
+        if (stages == 7) kern = experiment == 1 ? tc2::net_tower_pair_kernel<1, 7> : experiment == 3 ? tc2::net_tower_pair_kernel<3, 7>
+                              : experiment == 4 ? tc2::net_tower_pair_kernel<4, 7> : tc2::net_tower_pair_kernel<0, 7>;
+        else kern = experiment == 1 ? tc2::net_tower_pair_kernel<1, 6> : experiment == 3 ? tc2::net_tower_pair_kernel<3, 6>
+                  : experiment == 4 ? tc2::net_tower_pair_kernel<4, 6> : tc2::net_tower_pair_kernel<0, 6>;
+        RZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2::smem_alloc(stages)));
     }
     tc::Params p;
     p.w0 = net->tc2_w0; p.w = net->tc2_w; p.ss = net->scale_shift; p.blob = net->blob;
@@ -503,14 +511,12 @@ int net_forward_tc2(rz_net* net, const uint64_t* own, const uint64_t* enemy, flo
     grid = (grid + 1) & ~1u;  // whole pairs; a surplus CTA runs dummy tiles
     if (grid > (uint32_t)num_sms()) grid = (uint32_t)num_sms() & ~1u;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc2::kThreads); cfg.dynamicSmemBytes = tc2::kSmemAlloc; cfg.stream = stream;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc2::kThreads); cfg.dynamicSmemBytes = tc2::smem_alloc(stages); cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (experiment == 1) RZ_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc2::net_tower_pair_kernel<1>, p));
-    else if (experiment == 3) RZ_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc2::net_tower_pair_kernel<3>, p));
-    else RZ_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc2::net_tower_pair_kernel<0>, p));
+    RZ_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
     RZ_LAUNCH_CHECK();
     return RZ_OK;
 }
