@@ -265,7 +265,7 @@ int rz_net_create(const rz_net_cfg* cfg, int device, rz_net** out) {
         e = cudaMalloc(&net->tc_w0, (size_t)4 * 256 * 8 * sizeof(__half));
         if (e == cudaSuccess && R > 0) e = cudaMalloc(&net->tc_w, (size_t)2 * R * 36 * 8 * 256 * 8 * sizeof(__half));
         if (e == cudaSuccess) e = cudaMalloc(&net->tc2_w0, (size_t)2 * 2 * 4 * 64 * 8 * sizeof(__half));
-        if (e == cudaSuccess && R > 0) e = cudaMalloc(&net->tc2_w, (size_t)2 * R * 72 * 2 * 4096 * sizeof(__half));
+        if (e == cudaSuccess && R > 0) e = cudaMalloc(&net->tc2_w, (size_t)2 * R * 36 * 2 * 8192 * sizeof(__half));
     }
     if (e != cudaSuccess) {
         set_error("rz_net_create: cudaMalloc failed: %s", cudaGetErrorString(e));

@@ -26,7 +26,7 @@ struct rz_net {
     __half* tc_w;        // [2R layers][36 stages][8 kc][256 n][8] fp16: one 32 KB shared-memory image per pipeline stage
     // pair kernel (rz_net_tc2.cu, cta_group::2): the same weights in the order its K / N loops consume them
     __half* tc2_w0;      // [cta 2][nh 2][kc 4][n 64][8]
-    __half* tc2_w;       // [2R layers][72 stages][cta 2][kc 8][n 64][8]: one 8 KB image per CTA and pipeline stage
+    __half* tc2_w;       // [2R layers][36 stages][cta 2][kbl 2][kc 8][n 64][8]: one 16 KB image per CTA and pipeline stage
     // scratch for the host-buffer predict path
     void* scratch;
     size_t scratch_bytes;

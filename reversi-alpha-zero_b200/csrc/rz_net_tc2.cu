@@ -38,9 +38,12 @@ constexpr int kThreads = 320;  // warp 0 weight producer, warp 1 MMA issuer (lea
 constexpr int kEpiThreads = 256;
 constexpr uint32_t kActCg = 2896, kActSlot = 144;
 constexpr uint32_t kHalfBytes = 16 * kActCg;  // 46,336: 128 channels of the operand
-constexpr uint32_t kStageBytes = 8192;                // per CTA: one tap x 64 input channels x 64 of the 128 output channels
-constexpr uint32_t kMaxStages = 7;                    // ring depth is a template parameter (6 or 7), the ring sits last
-constexpr uint32_t kStagesPerLayer = 72;              // 2 output halves x 2 input halves x 9 taps x 2 blocks of 64 channels
+constexpr uint32_t kStageBytes = 16384;               // per CTA: one tap x 128 input channels x 64 of the 128 output channels
+constexpr uint32_t kMaxStages = 3;                    // ring depth (template parameter); the ring sits last
+constexpr uint32_t kStagesPerLayer = 36;              // 2 output halves x 2 input halves x 9 taps
+// (A first version used 8 KB stages of four MMAs: correct, but the issuing thread then spends longer on a stage's barrier
+//  wait + commit than the tensor pipe on its four 64-cycle MMAs -- 50 ms per launch, 25 ms with the waits removed,
+//  profiles/tower_v2_experiments_r02.log.  Eight MMAs per wait, and the next stage's barrier tested before they are issued.)
 constexpr uint32_t kA0Bytes = 8192, kW0Bytes = 8192;
 constexpr uint32_t kOffAct = 0;                       // half-buffers A (0), B (1), C (2)
 constexpr uint32_t kOffA0 = kOffAct + 3 * kHalfBytes;
@@ -75,6 +78,18 @@ __device__ __forceinline__ void umma2_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                  "h"((uint16_t)3)
                  : "memory");
+}
+// non-blocking test of a barrier phase
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
 }
 // arrive on the barrier at the same offset in CTA `rank` of the cluster.  Plain (default-semantics) arrive and wait, as the
 // 2-SM GEMM pipelines use them: a first version with .release.cluster arrives and .acquire.cluster waits was correct but
@@ -157,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
         if (lane == 0 && leader) {
             // ===== MMA issuer (leader CTA) ===================================================================
             uint32_t stage = 0, phase = 0, a0_par = 0, x_par[2] = {0, 0};
-            bool first = true;
+            bool first = true, ready = false;
             for (uint32_t it = 0; it < iters; ++it) {
                 // layer 0: [128 rows x 32] im2col tile per CTA x [32 x 128] per output half
                 mbar_wait(bar_a0, a0_par);
@@ -186,19 +201,21 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
                             for (uint32_t tap = 0; tap < 9; ++tap) {
                                 // tap (kh, kw) reads input pixel (y + kh - 1, x + kw - 1): slot offset 2*kh, chunk offset kw
                                 const uint32_t a_tap = xb + (2 * (tap / 3)) * kActSlot + (tap % 3) * 16;
-                                for (uint32_t kbl = 0; kbl < 2; ++kbl) {
-                                    if (EXP != 3) {
-                                        mbar_wait(bar_full(stage), phase);
-                                        tc_fence_after();
-                                    }
-                                    const uint32_t b_st = base + kOffW + stage * kStageBytes;
+                                if (EXP != 3) {
+                                    if (!ready) mbar_wait(bar_full(stage), phase);
+                                    tc_fence_after();
+                                }
+                                const uint32_t b_st = base + kOffW + stage * kStageBytes;
+                                const uint32_t cur = stage;
+                                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                                if (EXP != 3) ready = mbar_test(bar_full(stage), phase);   // the answer arrives while the MMAs below are issued
+#pragma unroll
+                                for (uint32_t kbl = 0; kbl < 2; ++kbl)
 #pragma unroll
                                     for (uint32_t j = 0; j < 4; ++j)
                                         umma2_f16(tmem + nh * 128, smem_desc(a_tap + (kbl * 8 + 2 * j) * kActCg, kActCg, kActSlot),
-                                                  smem_desc(b_st + 2 * j * 1024, 1024, 128), kIdesc, (kh | tap | kbl | j) != 0);
-                                    if (EXP != 3) umma2_commit(bar_empty(stage));
-                                    if (++stage == kStages) { stage = 0; phase ^= 1; }
-                                }
+                                                  smem_desc(b_st + kbl * 8192 + 2 * j * 1024, 1024, 128), kIdesc, (kh | tap | kbl | j) != 0);
+                                if (EXP != 3) umma2_commit(bar_empty(cur));
                             }
                         }
                         umma2_commit(bar_acc(nh));
@@ -455,15 +472,15 @@ __global__ void pack_w0_pair_kernel(const float* __restrict__ k0, __half* __rest
     const int co = nh * 128 + c * 64 + n;
     out[i] = __float2half_rn(k < 18 ? k0[(size_t)k * 256 + co] : 0.f);
 }
-// tower image: [layer][nh 2][kh 2][tap 9][kbl 2][cta 2][kc 8][n 64][8] fp16;
+// tower image: [layer][nh 2][kh 2][tap 9][cta 2][kbl 2][kc 8][n 64][8] fp16 (16 KB per CTA and stage);
 // input channel = kh*128 + kbl*64 + kc*8 + j, output channel = nh*128 + cta*64 + n
 __global__ void pack_w_pair_kernel(const float* __restrict__ blob, size_t off_res0, size_t stride, int n_layers, __half* __restrict__ out) {
-    const size_t total = (size_t)n_layers * kStagesPerLayer * 2 * 4096;
+    const size_t total = (size_t)n_layers * kStagesPerLayer * 2 * 8192;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int j = i & 7, n = (i >> 3) & 63, kc = (i >> 9) & 7, c = (i >> 12) & 1;
-        const size_t ls = i >> 13;                 // layer * 72 + stage
+        const int j = i & 7, n = (i >> 3) & 63, kc = (i >> 9) & 7, kbl = (i >> 12) & 1, c = (i >> 13) & 1;
+        const size_t ls = i >> 14;                 // layer * 36 + stage
         const int s = (int)(ls % kStagesPerLayer), l = (int)(ls / kStagesPerLayer);
-        const int kbl = s & 1, tap = (s >> 1) % 9, kh = ((s >> 1) / 9) & 1, nh = (s >> 1) / 18;
+        const int tap = s % 9, kh = (s / 9) & 1, nh = s / 18;
         const int ci = kh * 128 + kbl * 64 + kc * 8 + j, co = nh * 128 + c * 64 + n;
         out[i] = __float2half_rn(blob[off_res0 + (size_t)l * stride + ((size_t)tap * 256 + ci) * 256 + co]);
     }
@@ -484,18 +501,14 @@ int net_forward_tc2(rz_net* net, const uint64_t* own, const uint64_t* enemy, flo
     RZ_REQUIRE(net->cfg.filters == 256, "tcgen05 tower requires 256 filters");
     RZ_REQUIRE(net->cfg.value_fc <= (int)tc2::kMaxV, "tcgen05 tower supports value_fc_size <= %u", tc2::kMaxV);
     RZ_REQUIRE(n < (1ull << 31), "batch too large");
-    static int experiment = -1, stages = 6;
+    static int experiment = -1, stages = 3;
     typedef void (*kern_t)(const tc::Params);
     static kern_t kern = nullptr;
     if (experiment < 0) {
         const char* ex = getenv("RZ_TOWER_EXPERIMENT");
-        const char* st = getenv("RZ_TOWER_STAGES");
         experiment = ex ? atoi(ex) : 0;
-        stages = (st && atoi(st) == 7) ? 7 : 6;
-        if (stages == 7) kern = experiment == 1 ? tc2::net_tower_pair_kernel<1, 7> : experiment == 3 ? tc2::net_tower_pair_kernel<3, 7>
-                              : experiment == 4 ? tc2::net_tower_pair_kernel<4, 7> : tc2::net_tower_pair_kernel<0, 7>;
-        else kern = experiment == 1 ? tc2::net_tower_pair_kernel<1, 6> : experiment == 3 ? tc2::net_tower_pair_kernel<3, 6>
-                  : experiment == 4 ? tc2::net_tower_pair_kernel<4, 6> : tc2::net_tower_pair_kernel<0, 6>;
+        kern = experiment == 1 ? tc2::net_tower_pair_kernel<1, 3> : experiment == 3 ? tc2::net_tower_pair_kernel<3, 3>
+             : experiment == 4 ? tc2::net_tower_pair_kernel<4, 3> : tc2::net_tower_pair_kernel<0, 3>;
         RZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2::smem_alloc(stages)));
     }
     tc::Params p;
