@@ -39,17 +39,19 @@ constexpr int kEpiThreads = 256;
 constexpr uint32_t kActCg = 2896, kActSlot = 144;
 constexpr uint32_t kHalfBytes = 16 * kActCg;  // 46,336: 128 channels of the operand
 constexpr uint32_t kStageBytes = 16384;               // per CTA: one tap x 128 input channels x 64 of the 128 output channels
-constexpr uint32_t kMaxStages = 3;                    // ring depth (template parameter); the ring sits last
+constexpr uint32_t kMaxStages = 4;                    // ring depth (template parameter: 3 or 4); the ring sits last
 constexpr uint32_t kStagesPerLayer = 36;              // 2 output halves x 2 input halves x 9 taps
 // (A first version used 8 KB stages of four MMAs: correct, but the issuing thread then spends longer on a stage's barrier
 //  wait + commit than the tensor pipe on its four 64-cycle MMAs -- 50 ms per launch, 25 ms with the waits removed,
 //  profiles/tower_v2_experiments_r02.log.  Eight MMAs per wait, and the next stage's barrier tested before they are issued.)
 constexpr uint32_t kA0Bytes = 8192, kW0Bytes = 8192;
 constexpr uint32_t kOffAct = 0;                       // half-buffers A (0), B (1), C (2)
-constexpr uint32_t kOffA0 = kOffAct + 3 * kHalfBytes;
-constexpr uint32_t kOffW0 = kOffA0 + kA0Bytes;
+constexpr uint32_t kOffW0 = kOffAct + 3 * kHalfBytes;
 constexpr uint32_t kOffSS = kOffW0 + kW0Bytes;           // 2 x [scale 256][shift 256] fp32
-constexpr uint32_t kOffPart = kOffSS + 2 * 2048;         // [2 column sub-halves][128 rows][4] fp32 head partial sums
+// the layer-0 operand (8 KB, live from a tile's first instruction to its layer-0 MMAs) shares its bytes with the head
+// scratch (live during a tile's last phase): that buys the fourth weight stage
+constexpr uint32_t kOffA0 = kOffSS + 2 * 2048;
+constexpr uint32_t kOffPart = kOffA0;                    // [2 column sub-halves][128 rows][4] fp32 head partial sums
 constexpr uint32_t kOffHp = kOffPart + 2 * 128 * 4 * 4;  // [2 boards][128]
 constexpr uint32_t kOffHv = kOffHp + 2 * 128 * 4;        // [2][64]
 constexpr uint32_t kOffLogit = kOffHv + 2 * 64 * 4;      // [2][64]
@@ -61,6 +63,7 @@ constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr uint32_t kOffW = (kOffTmemPtr + 16 + 127) & ~127u;   // weight ring
 constexpr uint32_t smem_alloc(uint32_t stages) { return kOffW + stages * kStageBytes + 128; }  // + slack for manual 128 B alignment
 static_assert(smem_alloc(kMaxStages) <= 232448, "shared memory budget exceeded");
+static_assert(kOffFc1 + 2 * kMaxV * 4 - kOffA0 >= kA0Bytes, "head scratch must cover the layer-0 operand");
 
 // instruction descriptor, kind::f16: D = f32, A = B = f16, K-major both, N = 128, M = 256 (cta_group::2)
 constexpr uint32_t kIdesc = (1u << 4) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
@@ -259,6 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
             const uint32_t pos0 = tile * 2;
             const bool valid = pos0 + brd < p.n;
             // ---- layer-0 operand: im2col of the two bit planes, K index = tap*2 + plane, padded to 32 ----
+            epi_bar();   // the operand shares its bytes with the head scratch the other warps may still be reading (previous tile)
             {
                 const u64 o = valid ? p.own[pos0 + brd] : 0, e = valid ? p.enemy[pos0 + brd] : 0;
 #pragma unroll
@@ -501,14 +505,18 @@ int net_forward_tc2(rz_net* net, const uint64_t* own, const uint64_t* enemy, flo
     RZ_REQUIRE(net->cfg.filters == 256, "tcgen05 tower requires 256 filters");
     RZ_REQUIRE(net->cfg.value_fc <= (int)tc2::kMaxV, "tcgen05 tower supports value_fc_size <= %u", tc2::kMaxV);
     RZ_REQUIRE(n < (1ull << 31), "batch too large");
-    static int experiment = -1, stages = 3;
+    static int experiment = -1, stages = 4;
     typedef void (*kern_t)(const tc::Params);
     static kern_t kern = nullptr;
     if (experiment < 0) {
         const char* ex = getenv("RZ_TOWER_EXPERIMENT");
+        const char* st = getenv("RZ_TOWER_STAGES");
         experiment = ex ? atoi(ex) : 0;
-        kern = experiment == 1 ? tc2::net_tower_pair_kernel<1, 3> : experiment == 3 ? tc2::net_tower_pair_kernel<3, 3>
-             : experiment == 4 ? tc2::net_tower_pair_kernel<4, 3> : tc2::net_tower_pair_kernel<0, 3>;
+        stages = (st && atoi(st) == 3) ? 3 : 4;
+        if (stages == 3) kern = experiment == 1 ? tc2::net_tower_pair_kernel<1, 3> : experiment == 3 ? tc2::net_tower_pair_kernel<3, 3>
+                              : experiment == 4 ? tc2::net_tower_pair_kernel<4, 3> : tc2::net_tower_pair_kernel<0, 3>;
+        else kern = experiment == 1 ? tc2::net_tower_pair_kernel<1, 4> : experiment == 3 ? tc2::net_tower_pair_kernel<3, 4>
+                  : experiment == 4 ? tc2::net_tower_pair_kernel<4, 4> : tc2::net_tower_pair_kernel<0, 4>;
         RZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2::smem_alloc(stages)));
     }
     tc::Params p;
