@@ -76,6 +76,45 @@ __device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// the same with the descriptors as (low, high) words: the issue loop keeps the high words (LBO / SBO / layout bits) constant
+// and only ADDS to the start-address field of the low words -- with N = 128 an MMA lasts 64 cycles, so the dozen uniform
+// instructions the compiler spends on rebuilding a descriptor from an address (add, shift, mask, or, twice) would make
+// the single issuing thread, not the tensor pipe, the bottleneck
+__device__ __forceinline__ void umma2_f16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// warp-convergent variants: executed by all 32 lanes of the MMA warp, one elected lane issues.  (Issued from a divergent
+// `if (lane == 0)` region the compiler wraps every tcgen05 instruction in an ELECT / branch loop of its own.)
+__device__ __forceinline__ void umma2_f16_elect(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_commit_elect(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(bar),
+        "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr, uint32_t lbo) { return ((addr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo) { return ((sbo >> 4) & 0x3FFFu) | (1u << 14); }
 // completion of all prior cta_group::2 MMAs -> one arrival on the barrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma2_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
@@ -172,8 +211,8 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && leader) {
-            // ===== MMA issuer (leader CTA) ===================================================================
+        if (leader) {
+            // ===== MMA issuer (leader CTA): the whole warp runs the loop, one elected lane issues ================
             uint32_t stage = 0, phase = 0, a0_par = 0, x_par[2] = {0, 0};
             bool first = true, ready = false;
             for (uint32_t it = 0; it < iters; ++it) {
@@ -186,9 +225,9 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
                 for (uint32_t nh = 0; nh < 2; ++nh) {
 #pragma unroll
                     for (uint32_t j = 0; j < 2; ++j)
-                        umma2_f16(tmem + nh * 128, smem_desc(base + kOffA0 + j * 2 * 2048, 2048, 128),
-                                  smem_desc(base + kOffW0 + nh * 4096 + j * 2 * 1024, 1024, 128), kIdesc, j);
-                    umma2_commit(bar_acc(nh));
+                        umma2_f16_elect(tmem + nh * 128, desc_lo(base + kOffA0 + j * 2 * 2048, 2048), desc_hi(128),
+                                        desc_lo(base + kOffW0 + nh * 4096 + j * 2 * 1024, 1024), desc_hi(128), kIdesc, j);
+                    umma2_commit_elect(bar_acc(nh));
                 }
                 for (int l = 1; l < L; ++l) {
                     const uint32_t x0 = base + kOffAct + ((l & 1) ? 0u : 2u) * kHalfBytes;   // channels 0-127 of this layer's input
@@ -212,16 +251,17 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
                                 const uint32_t cur = stage;
                                 if (++stage == kStages) { stage = 0; phase ^= 1; }
                                 if (EXP != 3) ready = mbar_test(bar_full(stage), phase);   // the answer arrives while the MMAs below are issued
+                                const uint32_t a_lo = desc_lo(a_tap, kActCg), b_lo = desc_lo(b_st, 1024);
 #pragma unroll
                                 for (uint32_t kbl = 0; kbl < 2; ++kbl)
 #pragma unroll
                                     for (uint32_t j = 0; j < 4; ++j)
-                                        umma2_f16(tmem + nh * 128, smem_desc(a_tap + (kbl * 8 + 2 * j) * kActCg, kActCg, kActSlot),
-                                                  smem_desc(b_st + kbl * 8192 + 2 * j * 1024, 1024, 128), kIdesc, (kh | tap | kbl | j) != 0);
-                                if (EXP != 3) umma2_commit(bar_empty(cur));
+                                        umma2_f16_elect(tmem + nh * 128, a_lo + ((kbl * 8 + 2 * j) * kActCg >> 4), desc_hi(kActSlot),
+                                                        b_lo + ((kbl * 8192 + 2 * j * 1024) >> 4), desc_hi(128), kIdesc, (kh | tap | kbl | j) != 0);
+                                if (EXP != 3) umma2_commit_elect(bar_empty(cur));
                             }
                         }
-                        umma2_commit(bar_acc(nh));
+                        umma2_commit_elect(bar_acc(nh));
                     }
                 }
             }
