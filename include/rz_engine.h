@@ -116,7 +116,7 @@ typedef struct rz_net_cfg {
 
 /* Which kernel serves RZ_NET_IMPL_TCGEN05 from now on (process-wide): 1 = one CTA per tile (csrc/rz_net_tc.cu),
  * 2 = CTA pairs, cta_group::2, epilogue overlapped with the MMA stream (csrc/rz_net_tc2.cu).  The default comes from
- * the environment variable RZ_TOWER_KERNEL when the first network call is made.  Used by the tests and benchmarks to
+ * the environment variable RZ_TOWER_KERNEL when the first network call is made (default 2).  Used by the tests and benchmarks to
  * run both on the same inputs. */
 int rz_net_set_tower_kernel(int version);
 int rz_net_create(const rz_net_cfg* cfg, int device, rz_net** out);

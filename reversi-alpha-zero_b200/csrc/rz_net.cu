@@ -223,7 +223,7 @@ static int g_tower_kernel = 0;
 int tower_kernel_version() {
     if (g_tower_kernel == 0) {
         const char* s = getenv("RZ_TOWER_KERNEL");
-        g_tower_kernel = (s && atoi(s) == 2) ? 2 : 1;
+        g_tower_kernel = (s && atoi(s) == 1) ? 1 : 2;   // default: the CTA-pair kernel (30.9 ms vs 35.2 ms per 32 768 positions)
     }
     return g_tower_kernel;
 }

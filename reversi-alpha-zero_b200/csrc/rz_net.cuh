@@ -54,7 +54,7 @@ int net_forward_tc2(rz_net* net, const uint64_t* own, const uint64_t* enemy, flo
                     float* dbg_vlogit = nullptr);
 int net_pack_tc2(rz_net* net, cudaStream_t stream);
 // which tcgen05 tower kernel serves RZ_NET_IMPL_TCGEN05: 2 = CTA pairs with overlapped epilogue (default), 1 = one CTA per
-// tile (RZ_TOWER_KERNEL=1)
+// tile (RZ_TOWER_KERNEL=1, rz_net_set_tower_kernel)
 int tower_kernel_version();
 int net_forward(rz_net* net, const uint64_t* own, const uint64_t* enemy, float* policy, float* value, size_t n, int impl,
                 cudaStream_t stream);
