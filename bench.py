@@ -163,7 +163,8 @@ def run_reference(args):
     line = dict(impl="reference", metric="self_play_games_per_sec", value=gps, unit="games/s", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=budget * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", config=workload_config(args, cores=cores), node_expansions_per_sec=eps,
-                cpu_baseline=dict(value=gps, unit="games/s", cores=cores, kind="port", sample=sample),
+                cpu_baseline=dict(value=gps, unit="games/s", cores=cores, kind="port", sample=sample, value_per_core=gps / max(1, cores),
+                                  port_vs_unmodified_reference=port_calibration()),
                 e2e=dict(value=gps, unit="games/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     _emit(json.dumps(line))
 
@@ -241,6 +242,7 @@ def main():
                          disable_resignation_rate=0.1, **PLAY_KW)
 
     if args.full_games:
+        args.games = args.full_games   # the workload text reports the slots this calibration run really used
         cfg = E.engine_cfg_from_play_config(pp, games=args.full_games, seed=20260922, eval_mode=E.EVAL_NET, max_games=args.full_games)
         eng = E.Engine(cfg, net, local)
         t0 = time.perf_counter()

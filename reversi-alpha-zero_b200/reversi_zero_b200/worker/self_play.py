@@ -392,6 +392,12 @@ class SelfPlayWorker:
                                             (max_games is not None and finished >= max_games) or
                                             (max_waves is not None and waves_done >= max_waves))
                 if check:
+                    # agent/api.py:80-83: at every model check the reference's prediction server logs its mean batch size
+                    last = getattr(self, "_batch_stats", (0, 0))
+                    cur = (st.get("expansions", 0), st.get("nn_launches", 0))
+                    if self.engine is eng and cur[1] > last[1]:
+                        logger.debug(f"average_prediction_size={(cur[0] - last[0]) / (cur[1] - last[1]):.1f}")
+                    self._batch_stats = cur if self.engine is eng else (0, 0)
                     self.try_reload_model(check_now=True)
                 if stop:
                     break
