@@ -196,3 +196,31 @@ def test_tcgen05_matches_generic_on_device():
         torch.cuda.synchronize()
         outs.append((d_pol.cpu().numpy(), d_val.cpu().numpy()))
     assert np.abs(outs[0][0] - outs[1][0]).max() <= 1e-3 and np.abs(outs[0][1] - outs[1][1]).max() <= 1e-3
+
+
+def test_both_tower_kernels_vs_oracle():
+    """The two tcgen05 tower kernels -- CTA pairs with the epilogue overlapped (csrc/rz_net_tc2.cu, the default) and one CTA
+    per tile (csrc/rz_net_tc.cu, RZ_TOWER_KERNEL=1) -- on the same inputs: each within 1e-3 of the fp32 oracle on logits,
+    value logit, probabilities and value (ch5 `--new` weights, ragged batch), deterministic, and within 1e-3 of each other
+    (they differ only in the order of the fp32 accumulation: the pair kernel sums input channels 0-127 of all taps first)."""
+    mc = M.ModelConfig(**CH5)
+    w = M.build_random_weights(mc, 4)
+    own, enemy = selfplay_positions(301, 4)
+    planes = onn.planes_from_bitboards(own, enemy)
+    ref = dict(zip(("policy", "value", "logits", "vlogit", "tower"), onn.forward_logits(w, planes, 10)))
+    net = N.Net(mc)
+    net.load_weights(w)
+    out = {}
+    try:
+        for v in (1, 2):
+            N.set_tower_kernel(v)
+            a, b = _heads_on_device(net, own, enemy, want_tower=False), _heads_on_device(net, own, enemy, want_tower=False)
+            assert all(np.array_equal(a[k], b[k]) for k in a), v
+            for k in ("logits", "vlogit", "policy", "value"):
+                assert np.abs(a[k] - ref[k]).max() <= 1e-3, (v, k, np.abs(a[k] - ref[k]).max())
+            out[v] = a
+    finally:
+        N.set_tower_kernel(2)
+    for k in ("logits", "vlogit", "policy", "value"):
+        assert np.abs(out[1][k] - out[2][k]).max() <= 1e-3, k
+    net.close()
