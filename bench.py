@@ -282,6 +282,8 @@ def main():
         return eng
 
     eng = make_engine(args.groups, 20260922)
+    free_b, total_b = torch.cuda.mem_get_info(local)
+    hbm_used_gb = (total_b - free_b) / 1e9       # engine arenas + network + CUDA context, with the timed engine resident
     eng.run(max_waves=args.warmup * wps)
     s0 = eng.stats()
     sampler = ClockSampler(local)
@@ -411,7 +413,7 @@ def main():
     line = dict(metric="self_play_games_per_sec", value=value, unit="games/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=run_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16",
                 data="synthetic (random-init ch5 weights, self-generated games)",
-                config=workload_config(args, waves_per_step=wps, games_finished_in_window=games,
+                config=workload_config(args, waves_per_step=wps, hbm_in_use_gb_rank0=hbm_used_gb, games_finished_in_window=games,
                                        value_definition="games finished inside the timed window / device time of the window",
                                        value_renewal_estimate=value_est, measured_over_estimate=value / value_est if value_est else None,
                                        plies_decided=plies, plies_per_sec_over_60=plies / secs / PLIES_PER_GAME,
