@@ -544,3 +544,34 @@ def test_engine_is_drained_and_recreated_when_a_new_force_sim_exceeds_the_arenas
     assert (second.cfg.simulation_num_per_move, second.cfg.arena_simulation_num) == (300, 300)
     assert second.cfg.first_game_id == first.produced                      # ids go on where the old engine stopped
     assert n == first.produced + second.produced >= 30 and w.local_idx == n
+
+
+def test_evaluator_promotion_keeps_the_keras_side_best_model(tmp_path):
+    """on promotion the challenger becomes the best model for every consumer (lib/model_helpler.py:22-28): the
+    engine-side blob AND, when the trainer put them into the directory, model_config.json / model_weight.h5 ->
+    model_best_config.json / model_best_weight.h5; remove_model removes the reference's two files + the blob and then the
+    directory (worker/evaluate.py:115-121) -- and refuses, like os.rmdir, to delete a directory holding anything else."""
+    from reversi_zero_b200.worker.evaluate import EvaluateWorker, NEXT_GENERATION_BLOB
+    cfg = Config(project_dir=str(tmp_path), data_dir=str(tmp_path / "data"))
+    cfg.resource.create_directories()
+    rc = cfg.resource
+    d = os.path.join(rc.next_generation_model_dir, rc.next_generation_model_dirname_tmpl % "20260923-000000.000000")
+    os.makedirs(d)
+    np.save(os.path.join(d, NEXT_GENERATION_BLOB), np.arange(4, dtype=np.float32))
+    open(os.path.join(d, rc.next_generation_model_config_filename), "w").write('{"challenger": true}')
+    open(os.path.join(d, rc.next_generation_model_weight_filename), "wb").write(b"challenger-h5")
+    open(rc.model_best_weight_path, "wb").write(b"old-best-h5")
+    w = EvaluateWorker(cfg)
+    w.save_as_best_model(d)
+    assert np.array_equal(np.load(rc.model_best_blob_path), np.arange(4, dtype=np.float32))
+    assert open(rc.model_best_weight_path, "rb").read() == b"challenger-h5"
+    assert open(rc.model_best_config_path).read() == '{"challenger": true}'
+    w.remove_model(d)
+    assert not os.path.exists(d)
+    # a directory with an unexpected file is not silently wiped
+    os.makedirs(d)
+    np.save(os.path.join(d, NEXT_GENERATION_BLOB), np.arange(4, dtype=np.float32))
+    open(os.path.join(d, "notes.txt"), "w").write("keep me")
+    with pytest.raises(OSError):
+        w.remove_model(d)
+    assert os.path.exists(os.path.join(d, "notes.txt"))
