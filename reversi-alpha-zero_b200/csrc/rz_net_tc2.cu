@@ -68,29 +68,10 @@ static_assert(kOffFc1 + 2 * kMaxV * 4 - kOffA0 >= kA0Bytes, "head scratch must c
 // instruction descriptor, kind::f16: D = f32, A = B = f16, K-major both, N = 128, M = 256 (cta_group::2)
 constexpr uint32_t kIdesc = (1u << 4) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
 
-__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// the same with the descriptors as (low, high) words: the issue loop keeps the high words (LBO / SBO / layout bits) constant
-// and only ADDS to the start-address field of the low words -- with N = 128 an MMA lasts 64 cycles, so the dozen uniform
-// instructions the compiler spends on rebuilding a descriptor from an address (add, shift, mask, or, twice) would make
-// the single issuing thread, not the tensor pipe, the bottleneck
-__device__ __forceinline__ void umma2_f16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
-                                               uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %2};\n\t"
-        "mov.b64 db, {%3, %4};\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
-        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
+// tcgen05.mma.cta_group::2 with the descriptors as (low, high) words: the issue loop keeps the high words (LBO / SBO / layout
+// bits) constant and only ADDS to the start-address field of the low words -- with N = 128 an MMA lasts 64 cycles, so the
+// dozen uniform instructions the compiler spends on rebuilding a descriptor from an address (add, shift, mask, or, twice)
+// would make the issuing thread, not the tensor pipe, the bottleneck.
 // warp-convergent variants: executed by all 32 lanes of the MMA warp, one elected lane issues.  (Issued from a divergent
 // `if (lane == 0)` region the compiler wraps every tcgen05 instruction in an ELECT / branch loop of its own.)
 __device__ __forceinline__ void umma2_f16_elect(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
@@ -115,12 +96,6 @@ __device__ __forceinline__ void umma2_commit_elect(uint32_t bar) {
 }
 __device__ __forceinline__ uint32_t desc_lo(uint32_t addr, uint32_t lbo) { return ((addr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); }
 __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo) { return ((sbo >> 4) & 0x3FFFu) | (1u << 14); }
-// completion of all prior cta_group::2 MMAs -> one arrival on the barrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma2_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-                 "h"((uint16_t)3)
-                 : "memory");
-}
 // non-blocking test of a barrier phase
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
     uint32_t ok;

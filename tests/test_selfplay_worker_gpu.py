@@ -113,3 +113,25 @@ def test_reversi_player_mirror_plays_a_game(tmp_path):
     black.finish_game(1); white.finish_game(-1)
     assert len(black.moves) % 8 == 0 and black.moves[0][2] == 1 and white.moves[-1][2] == -1
     assert env.turn <= 60 and env.winner is not None
+
+
+def test_force_sim_beyond_the_arenas_drains_and_recreates_the_engine(tmp_path):
+    """ADVICE r1 (high) on the real engine: the arenas are sized for the largest count of the schedule; a `.force-sim` value
+    beyond them makes the worker let the resident games finish (rz_engine_set_max_games(1)), harvest them, and create a new
+    engine sized for the new count whose game ids go on where the old one stopped -- nothing is swallowed, no game is lost."""
+    cfg = mini_config(tmp_path)
+    cfg.play.update(dict(thinking_loop=1, schedule_of_simulation_num_per_move=[[0, 8], [6, 12]]))
+    cfg.play_data.update(dict(nb_game_in_file=1, max_file_num=1000, enable_ggf_data=False))
+    w = SelfPlayWorker(cfg)
+    n1 = w.start(max_games=10)
+    first = w.engine
+    assert first.cfg.arena_simulation_num == 12 and cfg.play.simulation_num_per_move == 12     # the schedule took effect (8 -> 12 at game 6)
+    with open(cfg.resource.force_simulation_num_file, "wt") as f:
+        f.write("40")
+    n2 = w.start(max_games=12)
+    assert w.engine is not first and w.engine.cfg.simulation_num_per_move == 40 and w.engine.cfg.arena_simulation_num >= 40
+    assert w.engine.cfg.first_game_id >= n1                       # ids continue after everything the old engine played
+    assert n2 >= 12 and w.local_idx == n1 + n2
+    files = glob.glob(os.path.join(cfg.resource.play_data_dir, "play_*.json"))
+    assert len(files) == n1 + n2                                   # one file per game (no draws dropped: rate 0), none lost in the hand-over
+    assert int(open(cfg.resource.self_play_game_idx_file).read()) == n1 + n2
