@@ -57,6 +57,32 @@ def run(n=10_000_000, iters=100, warmup=5):
         ms = e0.elapsed_time(e1) / iters
         gbs = n * bytes_per / ms / 1e6
         res[name] = dict(ms=ms, gpos_per_s=n / ms / 1e6, gbs=gbs, frac_of_measured_hbm=gbs / hbm, bytes_per_position=bytes_per)
+    # fused environment step (rz_step_dev, env/reversi_env.py:42-85) on reachable-looking positions: every env plays pos if it
+    # is legal for black, else its lowest legal move (algorithmic bytes per SURVEY 8(d): 17 in + 25 out = 42 B / position)
+    legal = D.to_numpy_u64(d_out_check(lib, D, d_own, d_enemy, n))
+    low = (legal & (~legal + np.uint64(1)))
+    act = np.where(legal != 0, np.log2(np.maximum(low, 1).astype(np.float64)).astype(np.int8), np.int8(0)).astype(np.int8)
+    st = dict(black=D.to_device(own), white=D.to_device(enemy), nxt=D.to_device(np.ones(n, np.uint8)), turn=D.to_device(np.zeros(n, np.uint8)),
+              done=D.to_device(np.zeros(n, np.uint8)), win=D.to_device(np.zeros(n, np.uint8)), act=D.to_device(act), legal=D.empty(n, np.uint64))
+    call = lambda: lib.rz_step_dev(D.ptr(st["black"]), D.ptr(st["white"]), D.ptr(st["nxt"]), D.ptr(st["turn"]), D.ptr(st["done"]),
+                                   D.ptr(st["win"]), D.ptr(st["act"]), D.ptr(st["legal"]), n, D.stream_ptr(s))
+    master = {k: st[k].clone() for k in ("black", "white", "nxt", "turn", "done", "win")}
+    total = 0.0
+    reps = 12
+    for it in range(reps + 2):
+        for k, v in master.items():       # every timed launch steps the SAME fresh states (restored outside the timed region)
+            st[k].copy_(v)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        _cabi.check(call(), "rz_step_dev")
+        e1.record(s)
+        torch.cuda.synchronize()
+        if it >= 2:
+            total += e0.elapsed_time(e1)
+    ms = total / reps
+    res["step"] = dict(ms=ms, gpos_per_s=n / ms / 1e6, gbs=n * 42 / ms / 1e6, frac_of_measured_hbm=n * 42 / ms / 1e6 / hbm, bytes_per_position=42,
+                       note="single launches on fresh states (black to move, a legal move each), events around each launch")
     # CPU oracle on one core for scale
     from oracle import bitboard as ob
     t = time.time(); ob.find_correct_moves_batch(own[:2_000_000], enemy[:2_000_000]); dt = time.time() - t
