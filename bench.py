@@ -355,10 +355,14 @@ def main():
     elif world > 1:
         net2.load_blob_dev(t_blob)
     worker = SelfPlayWorker(cfg, net=net2, device=local, rank=rank, world_size=world)
-    n_e2e = worker.start(max_waves=args.steps * wps, threaded=not args.no_writer_thread)   # engine creation, waves, harvest, files
+    worker._make_engine()                                                                   # arenas for all resident games
+    torch.cuda.synchronize()
+    e2e_setup_secs = time.perf_counter() - t0                                               # weights H2D + packing + engine creation
+    n_e2e = worker.start(max_waves=args.steps * wps, threaded=not args.no_writer_thread)   # waves, harvest, files
     torch.cuda.synchronize()
     e2e_secs = time.perf_counter() - t0
     st_e2e = worker.engine.stats()
+    e2e_wave_secs = st_e2e["run_ms"] / 1e3
     e2e_exps = float(st_e2e["expansions"])
     file_bytes = worker.bytes_written
     n_files = len(worker.files_written)
@@ -425,7 +429,7 @@ def main():
                 e2e=dict(value=e2e_value, unit="games/s", h2d_bytes_per_step=int(n_blob * 4 / args.steps), d2h_bytes_per_step=int(d2h / args.steps),
                          play_data_bytes_written=int(file_bytes), play_data_files_written=int(n_files), games_harvested=n_e2e_all,
                          value_renewal_estimate=e2e_value_est, expansions=e2e_exps, seconds=e2e_secs,
-                         writer_thread=not args.no_writer_thread,
+                         writer_thread=not args.no_writer_thread, setup_seconds_rank0=e2e_setup_secs, device_seconds_in_waves_rank0=e2e_wave_secs,
                          what="wall clock of: host weight blob -> device + pack, engine creation, K steps of waves driven by "
                               "SelfPlayWorker.start() while its writer thread harvests finished games (D2H) and writes one "
                               "play_*.json per game + GGF records (ch5.yml output settings); value = games written / wall seconds"),
