@@ -268,7 +268,6 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
         float* logit = reinterpret_cast<float*>(sm + kOffLogit);
         float* fc1 = reinterpret_cast<float*>(sm + kOffFc1);
         const uint32_t row_off = (g + 2) * kActSlot + (x + 1) * 16;  // within a half-buffer, + cg * kActCg
-        const float* ssh = p.ss + (size_t)L * 512;
         uint32_t acc_par[2] = {0, 0};
         uint32_t ss_buf = 0;
 
@@ -278,30 +277,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
             const bool valid = pos0 + brd < p.n;
             // ---- layer-0 operand: im2col of the two bit planes, K index = tap*2 + plane, padded to 32 ----
             epi_bar();   // the operand shares its bytes with the head scratch the other warps may still be reading (previous tile)
-            {
-                const u64 o = valid ? p.own[pos0 + brd] : 0, e = valid ? p.enemy[pos0 + brd] : 0;
-#pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    const int kc = 2 * sub + kk;
-                    uint32_t w[4];
-#pragma unroll
-                    for (int jp = 0; jp < 4; ++jp) {
-                        uint32_t packed = 0;
-#pragma unroll
-                        for (int half = 0; half < 2; ++half) {
-                            const int k = kc * 8 + jp * 2 + half;
-                            uint32_t bit = 0;
-                            if (k < 18) {
-                                const int tap = k >> 1, yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-                                if (yy >= 0 && yy < 8 && xx >= 0 && xx < 8) bit = (uint32_t)((((k & 1) ? e : o) >> (yy * 8 + xx)) & 1ULL);
-                            }
-                            packed |= (bit ? 0x3C00u : 0u) << (16 * half);  // fp16 1.0
-                        }
-                        w[jp] = packed;
-                    }
-                    *reinterpret_cast<uint4*>(sm + kOffA0 + kc * 2048 + g * 128 + x * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-            }
+            build_layer0_operand(sm + kOffA0, valid ? p.own[pos0 + brd] : 0, valid ? p.enemy[pos0 + brd] : 0, 2 * sub, g, x, y);
             fence_proxy_async();
             mbar_arrive_cta(bar_a0, 0);   // also says: this thread has finished with the previous tile's accumulators
 
@@ -338,61 +314,14 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
                         if (is_conv2) tmem_ld32(tm_res + lane_sel + c0, r);
                     };
                     auto math = [&](int c2, uint32_t (&v)[32], uint32_t (&r)[32]) {
-                        const int c0 = h * 128 + sub * 64 + c2 * 32;
-                        if (is_conv2) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                v[j] = __float_as_uint(fmaxf(fmaf(__uint_as_float(v[j]), sc[c0 + j], sc[256 + c0 + j]) + __uint_as_float(r[j]), 0.f));
-                        } else if (keep_res || last) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                v[j] = __float_as_uint(fmaxf(fmaf(__uint_as_float(v[j]), sc[c0 + j], sc[256 + c0 + j]), 0.f));
-                        } else {  // first conv of a block: only the fp16 operand is needed, ReLU happens in the convert
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), sc[c0 + j], sc[256 + c0 + j]));
-                        }
+                        epi_math(v, r, sc, h * 128 + sub * 64 + c2 * 32, is_conv2, keep_res || last);
                     };
                     auto store = [&](int c2, uint32_t (&v)[32]) {
                         const int c0 = h * 128 + sub * 64 + c2 * 32;
                         if (keep_res && !last) tmem_st32(tm_res + lane_sel + c0, v);
-                        if (!last) {
-                            const int cgl = sub * 8 + c2 * 4;   // channel group within the half-buffer
-#pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) {
-                                uint4 pk;
-                                if (keep_res) {
-                                    pk.x = pack_h2<false>(__uint_as_float(v[jj * 8 + 0]), __uint_as_float(v[jj * 8 + 1]));
-                                    pk.y = pack_h2<false>(__uint_as_float(v[jj * 8 + 2]), __uint_as_float(v[jj * 8 + 3]));
-                                    pk.z = pack_h2<false>(__uint_as_float(v[jj * 8 + 4]), __uint_as_float(v[jj * 8 + 5]));
-                                    pk.w = pack_h2<false>(__uint_as_float(v[jj * 8 + 6]), __uint_as_float(v[jj * 8 + 7]));
-                                } else {
-                                    pk.x = pack_h2<true>(__uint_as_float(v[jj * 8 + 0]), __uint_as_float(v[jj * 8 + 1]));
-                                    pk.y = pack_h2<true>(__uint_as_float(v[jj * 8 + 2]), __uint_as_float(v[jj * 8 + 3]));
-                                    pk.z = pack_h2<true>(__uint_as_float(v[jj * 8 + 4]), __uint_as_float(v[jj * 8 + 5]));
-                                    pk.w = pack_h2<true>(__uint_as_float(v[jj * 8 + 6]), __uint_as_float(v[jj * 8 + 7]));
-                                }
-                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(out + (cgl + jj) * kActCg), "r"(pk.x),
-                                             "r"(pk.y), "r"(pk.z), "r"(pk.w)
-                                             : "memory");
-                            }
-                        } else {
-                            // tower output: feed the 1x1 head convolutions directly from registers (fp32)
-                            const float* wp = p.blob + p.off_policy_conv;
-                            const float* wv = p.blob + p.off_value_conv;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const float a = __uint_as_float(v[j]);
-                                const float2 w2 = __ldg(reinterpret_cast<const float2*>(wp) + c0 + j);
-                                hp0 = fmaf(a, w2.x, hp0);
-                                hp1 = fmaf(a, w2.y, hp1);
-                                hvv = fmaf(a, __ldg(wv + c0 + j), hvv);
-                            }
-                            if (p.dbg_tower && valid) {
-                                float* d = p.dbg_tower + ((size_t)(pos0 + brd) * 64 + y * 8 + x) * 256 + c0;
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]);
-                            }
-                        }
+                        if (!last) epi_store_operand(v, out, sub * 8 + c2 * 4, keep_res);   // channel group within the half-buffer
+                        else epi_head_partial(v, c0, p, hp0, hp1, hvv,
+                                              (p.dbg_tower && valid) ? p.dbg_tower + ((size_t)(pos0 + brd) * 64 + y * 8 + x) * 256 : nullptr);
                     };
                     // the residual buffer rr is consumed by math(0) before prefetch(1) refills it
                     prefetch(0, va, rr);
@@ -409,68 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
                 }
             }
             // ---- heads (agent/model.py:43-56) on the 256 epilogue threads --------------------------------
-            part[(sub * 128 + m) * 4 + 0] = hp0;
-            part[(sub * 128 + m) * 4 + 1] = hp1;
-            part[(sub * 128 + m) * 4 + 2] = hvv;
-            epi_bar();
-            if (sub == 0) {
-                const float a0 = part[m * 4 + 0] + part[(128 + m) * 4 + 0];
-                const float a1 = part[m * 4 + 1] + part[(128 + m) * 4 + 1];
-                const float av = part[m * 4 + 2] + part[(128 + m) * 4 + 2];
-                const int pix = y * 8 + x;
-                hp[brd * 128 + pix] = fmaxf(fmaf(a0, ssh[0], ssh[2]), 0.f);        // Flatten is (C,H,W): index c*64 + pix
-                hp[brd * 128 + 64 + pix] = fmaxf(fmaf(a1, ssh[1], ssh[3]), 0.f);
-                hv[brd * 64 + pix] = fmaxf(fmaf(av, ssh[4], ssh[5]), 0.f);
-            }
-            epi_bar();
-            if (et < 128) {  // policy logits: Dense(128 -> 64)
-                const int b = et >> 6, j = et & 63;
-                const float* k = p.blob + p.off_policy_fc_k;
-                float acc = __ldg(p.blob + p.off_policy_fc_b + j);
-#pragma unroll 8
-                for (int i = 0; i < 128; ++i) acc = fmaf(hp[b * 128 + i], __ldg(k + i * 64 + j), acc);
-                logit[b * 64 + j] = acc;
-            }
-            for (int idx = et; idx < 2 * p.V; idx += kEpiThreads) {  // value Dense(64 -> V) + ReLU
-                const int b = idx / p.V, j = idx - b * p.V;
-                const float* k = p.blob + p.off_value_fc1_k;
-                float acc = __ldg(p.blob + p.off_value_fc1_b + j);
-#pragma unroll 8
-                for (int i = 0; i < 64; ++i) acc = fmaf(hv[b * 64 + i], __ldg(k + (size_t)i * p.V + j), acc);
-                fc1[b * kMaxV + j] = fmaxf(acc, 0.f);
-            }
-            epi_bar();
-            const int ew = warp - 2;
-            if (ew < 2) {  // softmax over 64 logits, one warp per board
-                const int b = ew;
-                const float l0 = logit[b * 64 + lane], l1 = logit[b * 64 + 32 + lane];
-                float mx = fmaxf(l0, l1);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
-                float s = e0 + e1;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (pos0 + b < p.n) {
-                    p.policy[(size_t)(pos0 + b) * 64 + lane] = e0 / s;
-                    p.policy[(size_t)(pos0 + b) * 64 + 32 + lane] = e1 / s;
-                    if (p.dbg_logits) {
-                        p.dbg_logits[(size_t)(pos0 + b) * 64 + lane] = l0;
-                        p.dbg_logits[(size_t)(pos0 + b) * 64 + 32 + lane] = l1;
-                    }
-                }
-            } else if (ew < 4) {  // value Dense(V -> 1) + tanh, one warp per board
-                const int b = ew - 2;
-                float acc = 0.f;
-                for (int j = lane; j < p.V; j += 32) acc = fmaf(fc1[b * kMaxV + j], __ldg(p.blob + p.off_value_fc2_k + j), acc);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                if (lane == 0 && pos0 + b < p.n) {
-                    const float pre = acc + __ldg(p.blob + p.off_value_fc2_b);
-                    p.value[pos0 + b] = tanhf(pre);
-                    if (p.dbg_vlogit) p.dbg_vlogit[pos0 + b] = pre;
-                }
-            }
+            heads_phase(p, hp0, hp1, hvv, sub, m, brd, y, x, et, warp - 2, lane, pos0, part, hp, hv, logit, fc1);
             // the next tile's layer-0 operand build only touches the A0 region, whose last reader (this tile's layer-0 MMAs)
             // completed before the first bar_acc of this tile
         }

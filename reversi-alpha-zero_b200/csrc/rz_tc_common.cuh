@@ -163,5 +163,164 @@ struct Params {
     int V;
 };
 
+// ---- pieces of the epilogue shared by the two tower kernels (rz_net_tc.cu, rz_net_tc2.cu) ----------------------------
+constexpr uint32_t kTcActCg = 2896;   // byte distance between channel groups of 8 in the operand layout
+constexpr uint32_t kTcMaxV = 512;
+
+// layer-0 operand (agent/model.py:30-33 first convolution as a GEMM): im2col of the two bit planes of one board row m =
+// (g, x), K index = tap * 2 + plane padded to 32, two of the four 8-wide K chunks (kc0, kc0 + 1) per calling thread;
+// a0 = the [4 kc][16 g][8 x][8] fp16 tile in shared memory
+__device__ __forceinline__ void build_layer0_operand(uint8_t* a0, u64 o, u64 e, int kc0, int g, int x, int y) {
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+        const int kc = kc0 + kk;
+        uint32_t w[4];
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {
+            uint32_t packed = 0;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int k = kc * 8 + jp * 2 + half;
+                uint32_t bit = 0;
+                if (k < 18) {
+                    const int tap = k >> 1, yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+                    if (yy >= 0 && yy < 8 && xx >= 0 && xx < 8) bit = (uint32_t)((((k & 1) ? e : o) >> (yy * 8 + xx)) & 1ULL);
+                }
+                packed |= (bit ? 0x3C00u : 0u) << (16 * half);  // fp16 1.0
+            }
+            w[jp] = packed;
+        }
+        *reinterpret_cast<uint4*>(a0 + kc * 2048 + g * 128 + x * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// folded BatchNorm (+ skip connection + ReLU) on 32 accumulator columns c0 .. c0 + 31 of one row; sc = [scale 256][shift 256].
+// conv2: second convolution of a block (adds the fp32 residual r, ReLU); relu_now: block outputs / the last layer (ReLU here);
+// otherwise the first convolution of a block, whose ReLU is folded into the fp16 convert of epi_store_operand
+__device__ __forceinline__ void epi_math(uint32_t (&v)[32], const uint32_t (&r)[32], const float* sc, int c0, bool conv2, bool relu_now) {
+    if (conv2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            v[j] = __float_as_uint(fmaxf(fmaf(__uint_as_float(v[j]), sc[c0 + j], sc[256 + c0 + j]) + __uint_as_float(r[j]), 0.f));
+    } else if (relu_now) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaxf(fmaf(__uint_as_float(v[j]), sc[c0 + j], sc[256 + c0 + j]), 0.f));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), sc[c0 + j], sc[256 + c0 + j]));
+    }
+}
+
+// 32 fp32 values of one row -> fp16, four 16-byte chunks (8 channels each) at row_addr + (cg0 + jj) * kTcActCg
+__device__ __forceinline__ void epi_store_operand(const uint32_t (&v)[32], uint32_t row_addr, int cg0, bool already_relu) {
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        uint4 pk;
+        if (already_relu) {
+            pk.x = pack_h2<false>(__uint_as_float(v[jj * 8 + 0]), __uint_as_float(v[jj * 8 + 1]));
+            pk.y = pack_h2<false>(__uint_as_float(v[jj * 8 + 2]), __uint_as_float(v[jj * 8 + 3]));
+            pk.z = pack_h2<false>(__uint_as_float(v[jj * 8 + 4]), __uint_as_float(v[jj * 8 + 5]));
+            pk.w = pack_h2<false>(__uint_as_float(v[jj * 8 + 6]), __uint_as_float(v[jj * 8 + 7]));
+        } else {
+            pk.x = pack_h2<true>(__uint_as_float(v[jj * 8 + 0]), __uint_as_float(v[jj * 8 + 1]));
+            pk.y = pack_h2<true>(__uint_as_float(v[jj * 8 + 2]), __uint_as_float(v[jj * 8 + 3]));
+            pk.z = pack_h2<true>(__uint_as_float(v[jj * 8 + 4]), __uint_as_float(v[jj * 8 + 5]));
+            pk.w = pack_h2<true>(__uint_as_float(v[jj * 8 + 6]), __uint_as_float(v[jj * 8 + 7]));
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + (cg0 + jj) * kTcActCg), "r"(pk.x), "r"(pk.y), "r"(pk.z),
+                     "r"(pk.w)
+                     : "memory");
+    }
+}
+
+// tower output columns c0 .. c0 + 31 of one row feed the 1x1 head convolutions from registers (policy: 2 filters, value: 1)
+__device__ __forceinline__ void epi_head_partial(const uint32_t (&v)[32], int c0, const Params& p, float& hp0, float& hp1, float& hvv,
+                                                 float* dbg_row /* nullable: this row's 256 tower outputs */) {
+    const float* wp = p.blob + p.off_policy_conv;
+    const float* wv = p.blob + p.off_value_conv;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float a = __uint_as_float(v[j]);
+        const float2 w2 = __ldg(reinterpret_cast<const float2*>(wp) + c0 + j);
+        hp0 = fmaf(a, w2.x, hp0);
+        hp1 = fmaf(a, w2.y, hp1);
+        hvv = fmaf(a, __ldg(wv + c0 + j), hvv);
+    }
+    if (dbg_row) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dbg_row[c0 + j] = __uint_as_float(v[j]);
+    }
+}
+
+// heads (agent/model.py:43-56) on the 256 epilogue threads of a CTA for its two boards: the per-thread partial sums of the
+// two column halves (colhalf 0 / 1 of row m) -> BN + ReLU -> Dense(128 -> 64) + softmax, Dense(64 -> V) + ReLU -> Dense(V -> 1)
+// + tanh.  part [2][128][4], hp [2][128], hv [2][64], logit [2][64], fc1 [2][kTcMaxV]: shared-memory scratch.
+__device__ __forceinline__ void heads_phase(const Params& p, float hp0, float hp1, float hvv, int colhalf, int m, int brd, int y, int x,
+                                            int et, int ew, int lane, uint32_t pos0, float* part, float* hp, float* hv, float* logit,
+                                            float* fc1) {
+    const float* ssh = p.ss + (size_t)p.n_layers * 512;
+    part[(colhalf * 128 + m) * 4 + 0] = hp0;
+    part[(colhalf * 128 + m) * 4 + 1] = hp1;
+    part[(colhalf * 128 + m) * 4 + 2] = hvv;
+    epi_bar();
+    if (colhalf == 0) {
+        const float a0 = part[m * 4 + 0] + part[(128 + m) * 4 + 0];
+        const float a1 = part[m * 4 + 1] + part[(128 + m) * 4 + 1];
+        const float av = part[m * 4 + 2] + part[(128 + m) * 4 + 2];
+        const int pix = y * 8 + x;
+        hp[brd * 128 + pix] = fmaxf(fmaf(a0, ssh[0], ssh[2]), 0.f);        // Flatten is (C,H,W): index c*64 + pix
+        hp[brd * 128 + 64 + pix] = fmaxf(fmaf(a1, ssh[1], ssh[3]), 0.f);
+        hv[brd * 64 + pix] = fmaxf(fmaf(av, ssh[4], ssh[5]), 0.f);
+    }
+    epi_bar();
+    if (et < 128) {  // policy logits: Dense(128 -> 64)
+        const int b = et >> 6, j = et & 63;
+        const float* k = p.blob + p.off_policy_fc_k;
+        float acc = __ldg(p.blob + p.off_policy_fc_b + j);
+#pragma unroll 8
+        for (int i = 0; i < 128; ++i) acc = fmaf(hp[b * 128 + i], __ldg(k + i * 64 + j), acc);
+        logit[b * 64 + j] = acc;
+    }
+    for (int idx = et; idx < 2 * p.V; idx += 256) {  // value Dense(64 -> V) + ReLU
+        const int b = idx / p.V, j = idx - b * p.V;
+        const float* k = p.blob + p.off_value_fc1_k;
+        float acc = __ldg(p.blob + p.off_value_fc1_b + j);
+#pragma unroll 8
+        for (int i = 0; i < 64; ++i) acc = fmaf(hv[b * 64 + i], __ldg(k + (size_t)i * p.V + j), acc);
+        fc1[b * kTcMaxV + j] = fmaxf(acc, 0.f);
+    }
+    epi_bar();
+    if (ew < 2) {  // softmax over 64 logits, one warp per board
+        const int b = ew;
+        const float l0 = logit[b * 64 + lane], l1 = logit[b * 64 + 32 + lane];
+        float mx = fmaxf(l0, l1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
+        float s = e0 + e1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (pos0 + b < p.n) {
+            p.policy[(size_t)(pos0 + b) * 64 + lane] = e0 / s;
+            p.policy[(size_t)(pos0 + b) * 64 + 32 + lane] = e1 / s;
+            if (p.dbg_logits) {
+                p.dbg_logits[(size_t)(pos0 + b) * 64 + lane] = l0;
+                p.dbg_logits[(size_t)(pos0 + b) * 64 + 32 + lane] = l1;
+            }
+        }
+    } else if (ew < 4) {  // value Dense(V -> 1) + tanh, one warp per board
+        const int b = ew - 2;
+        float acc = 0.f;
+        for (int j = lane; j < p.V; j += 32) acc = fmaf(fc1[b * kTcMaxV + j], __ldg(p.blob + p.off_value_fc2_k + j), acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0 && pos0 + b < p.n) {
+            const float pre = acc + __ldg(p.blob + p.off_value_fc2_b);
+            p.value[pos0 + b] = tanhf(pre);
+            if (p.dbg_vlogit) p.dbg_vlogit[pos0 + b] = pre;
+        }
+    }
+}
+
 }  // namespace tc
 }  // namespace rz
