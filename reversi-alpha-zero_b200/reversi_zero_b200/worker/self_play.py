@@ -357,7 +357,8 @@ class SelfPlayWorker:
 
     def start(self, max_games=None, max_seconds=None, max_waves=None, threaded=True):
         """Runs until max_games finished / max_seconds elapsed / max_waves executed (all None: forever, like the
-        reference).  Returns the number of games harvested by this call.  ``threaded=False`` harvests on the driving
+        reference).  Returns the number of games harvested by this call.  Engine requests the bookkeeping queued after the last
+        control point (e.g. a simulation count that needs new arenas) stay queued and are applied by the next call.  ``threaded=False`` harvests on the driving
         thread between two runs (the round-1 behaviour, kept for A/B measurements)."""
         if self.engine is None:
             self._make_engine()

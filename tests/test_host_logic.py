@@ -539,6 +539,9 @@ def test_engine_is_drained_and_recreated_when_a_new_force_sim_exceeds_the_arenas
     with open(cfg.resource.force_simulation_num_file, "wt") as f:
         f.write("300")
     n = w.start(max_games=30)
+    if w.engine is first:                     # request queued after the last control point: applied by the next start()
+        assert w._cmds
+        n += w.start(max_games=1)
     second = w.engine
     assert second is not first and first.closed and ("set_max_games", "MainThread", (1,)) in first.calls
     assert (second.cfg.simulation_num_per_move, second.cfg.arena_simulation_num) == (300, 300)

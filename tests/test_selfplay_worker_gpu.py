@@ -129,6 +129,11 @@ def test_force_sim_beyond_the_arenas_drains_and_recreates_the_engine(tmp_path):
     with open(cfg.resource.force_simulation_num_file, "wt") as f:
         f.write("40")
     n2 = w.start(max_games=12)
+    if w.engine is first:
+        # fast engine: the 12 games were over before the writer thread's request reached a control point; it stays queued and
+        # the next start() applies it at its first control point
+        assert w._cmds
+        n2 += w.start(max_games=1)
     assert w.engine is not first and w.engine.cfg.simulation_num_per_move == 40 and w.engine.cfg.arena_simulation_num >= 40
     assert w.engine.cfg.first_game_id >= n1                       # ids continue after everything the old engine played
     assert n2 >= 12 and w.local_idx == n1 + n2
