@@ -484,8 +484,9 @@ def test_writer_thread_harvests_while_the_driver_runs(tmp_path):
     assert int(open(cfg.resource.self_play_game_idx_file).read()) == n
     me = threading.current_thread().name
     assert all(thread == me for name, thread, _ in w.engine.calls)
-    assert ("set_simulation_num", me, (50,)) in w.engine.calls and cfg.play.simulation_num_per_move == 50
-    assert any(name == "set_resign_threshold" for name, _, _ in w.engine.calls)
+    # (a request queued after the last control point stays queued for the next start(); on a starved machine that may happen)
+    assert (("set_simulation_num", me, (50,)) in w.engine.calls or ("set_simulation_num", (50,)) in w._cmds) and cfg.play.simulation_num_per_move == 50
+    assert any(name == "set_resign_threshold" for name, _, _ in w.engine.calls) or any(name == "set_resign_threshold" for name, _ in w._cmds)
     assert w._writer is None                                               # joined
     # the single-threaded mode gives the same bookkeeping
     cfg2, w2 = make_worker(tmp_path / "b")
