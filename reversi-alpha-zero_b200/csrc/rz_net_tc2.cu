@@ -39,7 +39,7 @@ constexpr int kEpiThreads = 256;
 constexpr uint32_t kActCg = 2896, kActSlot = 144;
 constexpr uint32_t kHalfBytes = 16 * kActCg;  // 46,336: 128 channels of the operand
 constexpr uint32_t kStageBytes = 16384;               // per CTA: one tap x 128 input channels x 64 of the 128 output channels
-constexpr uint32_t kMaxStages = 4;                    // ring depth (template parameter: 3 or 4); the ring sits last
+constexpr uint32_t kMaxStages = 8;                    // ring slots (template: STAGES x SUB, at most 4 x 16 KB = 8 x 8 KB); the ring sits last
 constexpr uint32_t kStagesPerLayer = 36;              // 2 output halves x 2 input halves x 9 taps
 // (A first version used 8 KB stages of four MMAs: correct, but the issuing thread then spends longer on a stage's barrier
 //  wait + commit than the tensor pipe on its four 64-cycle MMAs -- 50 ms per launch, 25 ms with the waits removed,
@@ -62,7 +62,7 @@ constexpr uint32_t kNumBars = 2 * kMaxStages + 6;        // full, empty, w0, a0,
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr uint32_t kOffW = (kOffTmemPtr + 16 + 127) & ~127u;   // weight ring
 constexpr uint32_t smem_alloc(uint32_t stages) { return kOffW + stages * kStageBytes + 128; }  // + slack for manual 128 B alignment
-static_assert(smem_alloc(kMaxStages) <= 232448, "shared memory budget exceeded");
+static_assert(smem_alloc(4) <= 232448, "shared memory budget exceeded");
 static_assert(kOffFc1 + 2 * kMaxV * 4 - kOffA0 >= kA0Bytes, "head scratch must cover the layer-0 operand");
 
 // instruction descriptor, kind::f16: D = f32, A = B = f16, K-major both, N = 128, M = 256 (cta_group::2)
@@ -120,9 +120,12 @@ __device__ __forceinline__ void mbar_arrive_cta(uint32_t bar, uint32_t rank) {
 // protocol (time of the MMA stream + weight pipeline alone); 3 = no weight pipeline either (the MMA thread neither waits for
 // stages nor frees them, producer and relay idle: the bare issue rate of the MMA stream over whatever is in shared memory).
 // 4 = the leader does not wait for the peer's "my half has landed" relay (the cost of that hop).
-template <int EXP, int STAGES>
+// SUB = 2 splits every 16 KB stage into two 8 KB ring slots (one per block of 64 input channels) with their own barriers: a
+// slot is refilled as soon as ITS four MMAs have completed instead of after all eight of the stage.
+template <int EXP, int STAGES, int SUB>
 __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Params pp) {
-    constexpr uint32_t kStages = STAGES;
+    constexpr uint32_t kStages = STAGES * SUB;          // ring slots
+    constexpr uint32_t kSlotBytes = kStageBytes / SUB;
     Params p = pp;
     if (p.n_dev) p.n = *p.n_dev;
     extern __shared__ uint8_t smem_raw[];
@@ -176,12 +179,13 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
             for (uint32_t it = 0; it < (EXP == 3 ? 0u : iters); ++it) {
                 for (int l = 1; l < L; ++l) {
                     const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w) + ((size_t)(l - 1) * kStagesPerLayer * 2 + crank) * kStageBytes;
-                    for (uint32_t s = 0; s < kStagesPerLayer; ++s) {
-                        mbar_wait(bar_empty(stage), phase ^ 1);
-                        mbar_expect_tx(bar_full(stage), kStageBytes);
-                        bulk_g2s(base + kOffW + stage * kStageBytes, src + (size_t)s * 2 * kStageBytes, kStageBytes, bar_full(stage));
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
-                    }
+                    for (uint32_t s = 0; s < kStagesPerLayer; ++s)
+                        for (uint32_t q = 0; q < (uint32_t)SUB; ++q) {
+                            mbar_wait(bar_empty(stage), phase ^ 1);
+                            mbar_expect_tx(bar_full(stage), kSlotBytes);
+                            bulk_g2s(base + kOffW + stage * kSlotBytes, src + (size_t)s * 2 * kStageBytes + q * kSlotBytes, kSlotBytes, bar_full(stage));
+                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        }
                 }
             }
         }
@@ -218,22 +222,27 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
                             for (uint32_t tap = 0; tap < 9; ++tap) {
                                 // tap (kh, kw) reads input pixel (y + kh - 1, x + kw - 1): slot offset 2*kh, chunk offset kw
                                 const uint32_t a_tap = xb + (2 * (tap / 3)) * kActSlot + (tap % 3) * 16;
-                                if (EXP != 3) {
-                                    if (!ready) mbar_wait(bar_full(stage), phase);
-                                    tc_fence_after();
+                                const uint32_t a_lo = desc_lo(a_tap, kActCg);
+#pragma unroll
+                                for (uint32_t q = 0; q < (uint32_t)SUB; ++q) {
+                                    if (EXP != 3) {
+                                        if (!ready) mbar_wait(bar_full(stage), phase);
+                                        tc_fence_after();
+                                    }
+                                    const uint32_t b_lo = desc_lo(base + kOffW + stage * kSlotBytes, 1024);
+                                    const uint32_t cur = stage;
+                                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                                    if (EXP != 3) ready = mbar_test(bar_full(stage), phase);   // the answer arrives while the MMAs below are issued
+#pragma unroll
+                                    for (uint32_t kk = 0; kk < 2 / (uint32_t)SUB; ++kk) {
+                                        const uint32_t kbl = SUB == 2 ? q : kk;     // block of 64 input channels within the K half
+#pragma unroll
+                                        for (uint32_t j = 0; j < 4; ++j)
+                                            umma2_f16_elect(tmem + nh * 128, a_lo + ((kbl * 8 + 2 * j) * kActCg >> 4), desc_hi(kActSlot),
+                                                            b_lo + ((kk * 8192 + 2 * j * 1024) >> 4), desc_hi(128), kIdesc, (kh | tap | kbl | j) != 0);
+                                    }
+                                    if (EXP != 3) umma2_commit_elect(bar_empty(cur));
                                 }
-                                const uint32_t b_st = base + kOffW + stage * kStageBytes;
-                                const uint32_t cur = stage;
-                                if (++stage == kStages) { stage = 0; phase ^= 1; }
-                                if (EXP != 3) ready = mbar_test(bar_full(stage), phase);   // the answer arrives while the MMAs below are issued
-                                const uint32_t a_lo = desc_lo(a_tap, kActCg), b_lo = desc_lo(b_st, 1024);
-#pragma unroll
-                                for (uint32_t kbl = 0; kbl < 2; ++kbl)
-#pragma unroll
-                                    for (uint32_t j = 0; j < 4; ++j)
-                                        umma2_f16_elect(tmem + nh * 128, a_lo + ((kbl * 8 + 2 * j) * kActCg >> 4), desc_hi(kActSlot),
-                                                        b_lo + ((kbl * 8192 + 2 * j * 1024) >> 4), desc_hi(128), kIdesc, (kh | tap | kbl | j) != 0);
-                                if (EXP != 3) umma2_commit_elect(bar_empty(cur));
                             }
                         }
                         umma2_commit_elect(bar_acc(nh));
@@ -247,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Param
             mbar_arrive_cta(bar_w0, 0);
             for (uint32_t it = 0; it < (EXP == 3 ? 0u : iters); ++it)
                 for (int l = 1; l < L; ++l)
-                    for (uint32_t s = 0; s < kStagesPerLayer; ++s) {
+                    for (uint32_t s = 0; s < kStagesPerLayer * SUB; ++s) {
                         mbar_wait(bar_full(stage), phase);
                         if (EXP != 4) mbar_arrive_cta(bar_full(stage), 0);
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -393,13 +402,16 @@ int net_forward_tc2(rz_net* net, const uint64_t* own, const uint64_t* enemy, flo
     static kern_t kern = nullptr;
     if (experiment < 0) {
         const char* ex = getenv("RZ_TOWER_EXPERIMENT");
-        const char* st = getenv("RZ_TOWER_STAGES");
+        const char* st = getenv("RZ_TOWER_STAGES");   // "3": three 16 KB stages; "8": eight 8 KB slots; default four 16 KB stages
         experiment = ex ? atoi(ex) : 0;
-        stages = (st && atoi(st) == 3) ? 3 : 4;
-        if (stages == 3) kern = experiment == 1 ? tc2::net_tower_pair_kernel<1, 3> : experiment == 3 ? tc2::net_tower_pair_kernel<3, 3>
-                              : experiment == 4 ? tc2::net_tower_pair_kernel<4, 3> : tc2::net_tower_pair_kernel<0, 3>;
-        else kern = experiment == 1 ? tc2::net_tower_pair_kernel<1, 4> : experiment == 3 ? tc2::net_tower_pair_kernel<3, 4>
-                  : experiment == 4 ? tc2::net_tower_pair_kernel<4, 4> : tc2::net_tower_pair_kernel<0, 4>;
+        const int sv = st ? atoi(st) : 4;
+        stages = sv == 3 ? 3 : 4;
+        if (sv == 8) kern = experiment == 1 ? tc2::net_tower_pair_kernel<1, 4, 2> : experiment == 3 ? tc2::net_tower_pair_kernel<3, 4, 2>
+                          : tc2::net_tower_pair_kernel<0, 4, 2>;
+        else if (sv == 3) kern = experiment == 1 ? tc2::net_tower_pair_kernel<1, 3, 1> : experiment == 3 ? tc2::net_tower_pair_kernel<3, 3, 1>
+                               : tc2::net_tower_pair_kernel<0, 3, 1>;
+        else kern = experiment == 1 ? tc2::net_tower_pair_kernel<1, 4, 1> : experiment == 3 ? tc2::net_tower_pair_kernel<3, 4, 1>
+                  : experiment == 4 ? tc2::net_tower_pair_kernel<4, 4, 1> : tc2::net_tower_pair_kernel<0, 4, 1>;
         RZ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2::smem_alloc(stages)));
     }
     tc::Params p;
