@@ -470,11 +470,17 @@ struct WCtx {
             const float u = (float)u01(r0.x);
             int pre = 0;
             while (pre < 59 && u >= c.warm_cdf[pre]) ++pre;
-            for (int i = 0; i < pre && !sl.env.done; ++i) {
-                const bool b = sl.env.next_player == 1;
-                const u64 legal = find_correct_moves(b ? sl.env.black : sl.env.white, b ? sl.env.white : sl.env.black);
-                const U4 r = draw(c.seed, sl.game_id, 2 + (uint32_t)i, P_GAME, 0);
-                env_step(sl.env, nth_set_bit(legal, (int)(u01(r.x) * (double)popc64(legal))));
+            // a random playout that ends before turn `pre` is drawn again (another stream), so that late turns are not
+            // under-represented; after 8 failures the slot starts a fresh game
+            for (uint32_t attempt = 0; attempt < 8; ++attempt) {
+                env_reset(sl.env);
+                for (int i = 0; i < pre && !sl.env.done; ++i) {
+                    const bool b = sl.env.next_player == 1;
+                    const u64 legal = find_correct_moves(b ? sl.env.black : sl.env.white, b ? sl.env.white : sl.env.black);
+                    const U4 r = draw(c.seed, sl.game_id, 2 + (uint32_t)i + 64u * attempt, P_GAME, 0);
+                    env_step(sl.env, nth_set_bit(legal, (int)(u01(r.x) * (double)popc64(legal))));
+                }
+                if (!sl.env.done) break;
             }
             if (sl.env.done) env_reset(sl.env);
             else if (sl.env.turn > 0) {

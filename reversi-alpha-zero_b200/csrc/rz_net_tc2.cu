@@ -121,7 +121,9 @@ __device__ __forceinline__ void mbar_arrive_cta(uint32_t bar, uint32_t rank) {
 // stages nor frees them, producer and relay idle: the bare issue rate of the MMA stream over whatever is in shared memory).
 // 4 = the leader does not wait for the peer's "my half has landed" relay (the cost of that hop).
 // SUB = 2 splits every 16 KB stage into two 8 KB ring slots (one per block of 64 input channels) with their own barriers: a
-// slot is refilled as soon as ITS four MMAs have completed instead of after all eight of the stage.
+// slot is refilled as soon as ITS four MMAs have completed instead of after all eight of the stage.  Measured on one box
+// (profiles/tower_v2_experiments_r02.log): 4 x 16 KB 31.6 ms (default), 8 x 8 KB 34.5 ms (twice the waits / commits in the
+// issue loop cost more than the earlier refills gain), 3 x 16 KB 33.3 ms.
 template <int EXP, int STAGES, int SUB>
 __global__ void __launch_bounds__(kThreads, 1) net_tower_pair_kernel(const Params pp) {
     constexpr uint32_t kStages = STAGES * SUB;          // ring slots
