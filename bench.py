@@ -418,6 +418,7 @@ def main():
                 ms_per_step=run_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16",
                 data="synthetic (random-init ch5 weights, self-generated games)",
                 config=workload_config(args, waves_per_step=wps, hbm_in_use_gb_rank0=hbm_used_gb, games_finished_in_window=games,
+                                       games_finished_in_warmup_rank0=s0["games_finished"], waves_in_warmup=args.warmup * wps,
                                        value_definition="games finished inside the timed window / device time of the window",
                                        value_renewal_estimate=value_est, measured_over_estimate=value / value_est if value_est else None,
                                        plies_decided=plies, plies_per_sec_over_60=plies / secs / PLIES_PER_GAME,
