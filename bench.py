@@ -16,6 +16,10 @@ the measured waves-per-turn profile of complete games, profiles/full_games.json)
 count through the public worker (host weights -> device, SelfPlayWorker.start() with its writer thread,
 play_*.json + GGF files on disk) over wall-clock time.
 
+`other_baseline_configs` (rank 0, outside every timed region): BASELINE config 5 (legal-move / flip / step operators on
+10 M positions, GB/s vs the measured HBM peak) and config 4 (the same tower kernel on a 19-block network), so that they
+appear in the same driver-run record as the headline.
+
 Launch: python bench.py [--gpus N --steps K --warmup W] (N > 1 under torch.distributed.run, one rank per
 GPU).  `--impl reference` times the CPU port of the reference's own self-play worker (oracle/) on the host
 cores instead.  Prints ONE JSON line on rank 0.
@@ -190,6 +194,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--games", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the config-4 / config-5 side measurements on rank 0")
     ap.add_argument("--sims", type=int, default=400, help="simulation_num_per_move (BASELINE config 3 uses 800 with --games 8192)")
     ap.add_argument("--solver", action="store_true", help="with --full-games: ch5 default use_solver_turn = use_solver_turn_in_simulation = 50")
     ap.add_argument("--groups", type=int, default=0, help="engine overlap groups (0 = auto, 1 = no overlap: clean per-kernel timing)")
@@ -403,6 +408,25 @@ def main():
                     mcts_tick_share_of_step=roof["mcts_ms"] / max(1e-9, roof["run_ms"]),
                     measured_on="a second engine with overlap_groups=1 right after the timed region (events bracket single launches)")
 
+    # ---- the other BASELINE configurations that fit one GPU, measured in the same run (outside every timed region) ----
+    extra = {}
+    if not args.no_extra_configs:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        try:    # config 5: legal-move / flip microbench on 10 M positions resident in HBM (GB/s vs the measured HBM peak)
+            import k1_microbench
+            k1 = k1_microbench.run(iters=50, with_cpu=False)
+            extra["config5_k1_10M_positions"] = {k: dict(ms=v["ms"], gbs=v["gbs"], frac_of_measured_hbm=v["frac_of_measured_hbm"])
+                                                  for k, v in k1.items() if isinstance(v, dict)}
+        except Exception as ex:
+            extra["config5_k1_10M_positions"] = dict(error=repr(ex))
+        try:    # config 4: the same tower kernel on a 19-block network, 32 768 positions, 20 launches back to back
+            import nn_bench
+            r4 = nn_bench.run(32768, iters=20, warmup=3, res_blocks=19)
+            extra["config4_19block_tower"] = dict(ms=r4["ms"], tflops=r4["tflops"], frac_of_burst_peak=r4["frac_of_burst_peak"],
+                                                  frac_of_sustained_peak=r4["frac_of_sustained_peak"])
+        except Exception as ex:
+            extra["config4_19block_tower"] = dict(error=repr(ex))
+
     cb = None
     if not args.no_cpu_baseline:
         r, gps = cpu_baseline(budget_s=15.0)
@@ -434,7 +458,7 @@ def main():
                          what="wall clock of: host weight blob -> device + pack, engine creation, K steps of waves driven by "
                               "SelfPlayWorker.start() while its writer thread harvests finished games (D2H) and writes one "
                               "play_*.json per game + GGF records (ch5.yml output settings); value = games written / wall seconds"),
-                gpu_launches=int(launches))
+                gpu_launches=int(launches), other_baseline_configs=extra)
     _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -21,7 +21,7 @@ def d_out_check(lib, D, d_own, d_enemy, n):
     return out
 
 
-def run(n=10_000_000, iters=100, warmup=5):
+def run(n=10_000_000, iters=100, warmup=5, with_cpu=True):
     import torch
     from reversi_zero_b200 import _cabi, device as D
     peaks = {}
@@ -83,6 +83,10 @@ def run(n=10_000_000, iters=100, warmup=5):
     ms = total / reps
     res["step"] = dict(ms=ms, gpos_per_s=n / ms / 1e6, gbs=n * 42 / ms / 1e6, frac_of_measured_hbm=n * 42 / ms / 1e6 / hbm, bytes_per_position=42,
                        note="single launches on fresh states (black to move, a legal move each), events around each launch")
+    res["n"] = n
+    res["hbm_peak_gbs"] = hbm
+    if not with_cpu:
+        return res
     # CPU oracle on one core for scale
     from oracle import bitboard as ob
     t = time.time(); ob.find_correct_moves_batch(own[:2_000_000], enemy[:2_000_000]); dt = time.time() - t
