@@ -272,7 +272,7 @@ int rz_engine_stats(rz_engine* e, rz_stats* out);
 int rz_engine_set_max_games(rz_engine* e, uint64_t max_games);
 /* warm_start only: weight[t] (t = 0 .. n-1, n <= 60) is proportional to the time a game spends at turn t; the first
  * game of every slot then begins at turn t with probability weight[t] / sum and its first search runs a uniformly drawn
- * fraction of simulation_num_per_move, i.e. the slots start in the stationary state of an engine that has been running
+ * fraction of simulation_num_per_move (of the waves the profile gives the turn, where that is less), i.e. the slots start in the stationary state of an engine that has been running
  * for a long time (used by bench.py, which measures finished games per second over a window shorter than a game).
  * Without this call the turns 0..57 are equally likely.  Call before the first rz_engine_run. */
 int rz_engine_set_warm_start_profile(rz_engine* e, const float* weight, int n);

@@ -137,6 +137,7 @@ struct DevCfg {
     u64 seed, first_game_id, game_id_stride, max_games;
     uint32_t nodes_cap, edges_cap, hash_cap;  // per slot (hash_cap is a power of two)
     float warm_cdf[60];  // warm_start: P(first game of a slot begins at turn <= t), rz_engine_set_warm_start_profile
+    float warm_waves[60];  // ... and the waves a search at turn t takes in a long-running engine (0 = unknown)
 };
 
 struct DevPtrs {
@@ -414,7 +415,7 @@ int rz_engine_create(const rz_engine_cfg* cfg, rz_net* net, int device, rz_engin
     c.start_rethinking_turn = cfg->start_rethinking_turn; c.allowed_resign_turn = cfg->allowed_resign_turn;
     c.use_resign = cfg->use_resign_threshold; c.share = cfg->share_mtcs_info; c.max_plies = cfg->max_plies > 0 ? cfg->max_plies : 64;
     c.warm_start = cfg->warm_start;
-    for (int t = 0; t < 60; ++t) c.warm_cdf[t] = t < 58 ? (float)(t + 1) / 58.f : 1.f;  // default: turns 0..57 equally likely
+    for (int t = 0; t < 60; ++t) { c.warm_cdf[t] = t < 58 ? (float)(t + 1) / 58.f : 1.f; c.warm_waves[t] = 0.f; }  // default: turns 0..57 equally likely
     c.two_nets = 0;
     c.keep_games = cfg->reset_mtcs_info_per_game > 1 ? cfg->reset_mtcs_info_per_game : 1;
     c.solver_turn = cfg->use_solver_turn; c.solver_sim_turn = cfg->use_solver_turn_in_simulation;
@@ -602,6 +603,7 @@ int rz_engine_set_warm_start_profile(rz_engine* e, const float* weight, int n) {
     for (int t = 0; t < 60; ++t) {
         if (t < n) cum += weight[t];
         e->dc.warm_cdf[t] = t >= n - 1 ? 1.f : (float)(cum / total);
+        e->dc.warm_waves[t] = t < n ? weight[t] : 0.f;
     }
     return RZ_OK;
 }

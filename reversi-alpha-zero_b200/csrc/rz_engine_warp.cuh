@@ -487,8 +487,14 @@ struct WCtx {
                 const bool b = sl.env.next_player == 1;
                 begin_ply(b ? sl.env.black : sl.env.white, b ? sl.env.white : sl.env.black, sl.env.next_player);
                 if (sl.phase == PH_SEARCH) {
-                    // at least two simulations: the first one only expands the root, and a recorded ply needs a visit
-                    uint32_t part = (uint32_t)(u01(r0.y) * (double)c.S) + 1u;
+                    // The first search runs a uniformly drawn part of a whole one.  Late in the game a search of a long-running
+                    // engine is short in WAVES (its simulations end in terminal positions already in the tree: 24 instead of 50
+                    // waves at 400 simulations), while this slot's tree is empty and needs the network for every simulation, K per
+                    // wave: the part is drawn from the waves the profile gives the turn, so that the slot decides when its
+                    // steady-state twin would.  At least two simulations: the first one only expands the root.
+                    const double whole = (c.warm_waves[pre] > 0.f && (double)c.warm_waves[pre] * c.K < (double)c.S) ? (double)c.warm_waves[pre] * c.K
+                                                                                                               : (double)c.S;
+                    uint32_t part = (uint32_t)(u01(r0.y) * whole) + 1u;
                     if (part < 2u) part = 2u;
                     sl.sims_target = part < (uint32_t)c.S ? part : (uint32_t)c.S;
                 }
