@@ -88,6 +88,23 @@ def test_unaligned_views_vs_oracle():
         assert np.array_equal(zb.calc_flip_batch(p, o, e), ob.calc_flip_batch(p, o, e))
 
 
+def test_overlapping_inputs_follow_the_reference_arithmetic():
+    """own and enemy sharing squares is not a board, but lib/bitboard.py gives such input a definite answer (pure bit
+    arithmetic; its env even produces such boards when a move onto an occupied square flips something, reversi_env.py:56-63).
+    The bit-sliced kernels walk rays instead of rippling a carry, so they hand groups of 32 positions that contain an overlap
+    to the scalar code: the results must still be the oracle's, bit for bit."""
+    rng = np.random.default_rng(21)
+    n = 50_000
+    own = rng.integers(0, 2 ** 64, size=n, dtype=U64) & rng.integers(0, 2 ** 64, size=n, dtype=U64)
+    enemy = rng.integers(0, 2 ** 64, size=n, dtype=U64) & rng.integers(0, 2 ** 64, size=n, dtype=U64)
+    clean = rng.random(n) < 0.9                       # 90 % proper boards, the rest with shared squares: most groups of 32 are mixed
+    enemy[clean] &= ~own[clean]
+    pos = rng.integers(0, 64, size=n, dtype=np.uint8)
+    assert (own & enemy).any()
+    assert np.array_equal(zb.find_correct_moves_batch(own, enemy), ob.find_correct_moves_batch(own, enemy))
+    assert np.array_equal(zb.calc_flip_batch(pos, own, enemy), ob.calc_flip_batch(pos, own, enemy))
+
+
 def test_full_size_bit_exact_and_properties():
     n = 10_000_000  # BASELINE.json config 5
     own, enemy, pos = positions(20260922, n)
