@@ -94,9 +94,6 @@ uint64_t rz_dihedral_host(uint64_t x, int t);
  * one register per square): pos == NULL: out[i] = find_correct_moves(own[i], enemy[i]); else out[i] = calc_flip(pos[i], ..).
  * Same header compiled for the host; exists so that the formulation can be held against the oracle without a GPU. */
 int rz_bitsliced_host(const uint8_t* pos, const uint64_t* own, const uint64_t* enemy, uint64_t* out, size_t n);
-/* the same for the fused environment step (rz_step's arguments, host pointers, in place) */
-int rz_step_bitsliced_host(uint64_t* black, uint64_t* white, uint8_t* next_player, uint8_t* turn, uint8_t* done, uint8_t* winner,
-                           const int8_t* action, uint64_t* legal_out, size_t n);
 void rz_env_reset_host(rz_env_state* s);                                              /* reversi_env.py:26-32 */
 void rz_env_update_host(rz_env_state* s, uint64_t black, uint64_t white, int next_player); /* :34-40 */
 void rz_env_step_host(rz_env_state* s, int action /* -1 = None */);                   /* :42-74 */

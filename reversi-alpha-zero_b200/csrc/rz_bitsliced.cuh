@@ -173,18 +173,22 @@ RZ_HD void flips_half(const uint32_t* O, const uint32_t* E, const uint32_t* P, u
     transpose32(F);
 }
 
-// lib/bitboard.py:70-92 for 32 positions held by one thread; like the reference it ignores what stands on pos[i] itself
+// lib/bitboard.py:70-92 for 32 positions held by one thread; like the reference it ignores what stands on pos[i] itself.
+// own and enemy sharing a square is not a board, but the reference's carry-trick arithmetic gives such input a definite answer
+// (a run ends at the first NON-opponent square) that the ray walk does not reproduce: a group of 32 that contains such a
+// position goes through the scalar code -- here when CHECK_OVERLAP (host twin), in the kernels before they call this
+// (compact loops over the staged inputs, so that the hot path carries no 32-fold unrolled scalar code).
+RZ_HD bool any_overlap32(const u64* own, const u64* enemy) {
+    u64 overlap = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) overlap |= own[i] & enemy[i];
+    return overlap != 0;
+}
+template <bool CHECK_OVERLAP = true>
 RZ_HD void calc_flip32(const uint8_t* pos, const u64* own, const u64* enemy, u64* out) {
-    {   // own and enemy sharing a square is not a board, but the reference's carry-trick arithmetic gives such input a definite
-        // answer (the run ends at the first NON-opponent square) that the ray walk below does not reproduce: scalar code then
-        u64 overlap = 0;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) overlap |= own[i] & enemy[i];
-        if (overlap) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) out[i] = calc_flip(pos[i] & 63, own[i], enemy[i]);   // unrolled: the arrays stay in registers
-            return;
-        }
+    if (CHECK_OVERLAP && any_overlap32(own, enemy)) {
+        for (int i = 0; i < 32; ++i) out[i] = calc_flip(pos[i] & 63, own[i], enemy[i]);
+        return;
     }
     uint32_t O[64], E[64], P[64], F[32];
     {
@@ -214,196 +218,6 @@ RZ_HD void calc_flip32(const uint8_t* pos, const u64* own, const u64* enemy, u64
     flips_half<1>(O, E, P, F);
 #pragma unroll
     for (int i = 0; i < 32; ++i) out[i] |= (u64)F[i] << 32;
-}
-
-// Both directions +-(DX, DY) of calc_flip for 32 positions in ONE pass over all 64 squares, with the move plane decoded on
-// the fly from the 3 + 3 bit planes of the move square (P[k] = lo[k & 7] & hi[k >> 3]): used by step32, which needs the flip
-// planes themselves (not their transpose) and cannot afford a 64-register move plane next to own / enemy / flips.
-template <int DX, int DY>
-RZ_HD void flips_pair(const uint32_t* O, const uint32_t* E, const uint32_t* lo, const uint32_t* hi, uint32_t* F) {
-#pragma unroll
-    for (int s = 0; s < 64; ++s) {
-        const int x0 = s & 7, y0 = s >> 3;
-        const int px = x0 - DX, py = y0 - DY;
-        if (px >= 0 && px < 8 && py >= 0 && py < 8) continue;  // not the first square of its line
-        int n = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int x = x0 + i * DX, y = y0 + i * DY;
-            if (x >= 0 && x < 8 && y >= 0 && y < 8) n = i + 1;
-        }
-        if (n < 3) continue;
-        uint32_t P[8], f[8], g[8], fb[8], gb[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (i >= n) break;
-            const int cur = (x0 + i * DX) + 8 * (y0 + i * DY);
-            P[i] = lo[cur & 7] & hi[cur >> 3];
-        }
-        f[0] = 0; g[n - 1] = 0; fb[n - 1] = 0; gb[0] = 0;
-#pragma unroll
-        for (int i = 1; i < 8; ++i) {          // forward: opponent run that starts right after the move square
-            if (i >= n) break;
-            f[i] = E[(x0 + i * DX) + 8 * (y0 + i * DY)] & (P[i - 1] | f[i - 1]);
-        }
-#pragma unroll
-        for (int i = 6; i >= 0; --i) {         // backward
-            if (i > n - 2) continue;
-            fb[i] = E[(x0 + i * DX) + 8 * (y0 + i * DY)] & (P[i + 1] | fb[i + 1]);
-        }
-#pragma unroll
-        for (int i = 6; i >= 1; --i) {         // forward runs that are closed by an own disc
-            if (i > n - 2) continue;
-            g[i] = f[i] & (O[(x0 + (i + 1) * DX) + 8 * (y0 + (i + 1) * DY)] | g[i + 1]);
-        }
-#pragma unroll
-        for (int i = 1; i < 7; ++i) {          // backward runs closed by an own disc
-            if (i > n - 2) break;
-            gb[i] = fb[i] & (O[(x0 + (i - 1) * DX) + 8 * (y0 + (i - 1) * DY)] | gb[i - 1]);
-        }
-#pragma unroll
-        for (int i = 1; i < 7; ++i) {
-            if (i > n - 2) break;
-            F[(x0 + i * DX) + 8 * (y0 + i * DY)] |= g[i] | gb[i];
-        }
-    }
-}
-
-// One ReversiEnv.step (env/reversi_env.py:42-85, the same decisions as the scalar env_step in rz_bitboard.cuh) for 32
-// environments held by one thread: the board part.  In: black / white, bit masks over the 32 environments (btm: black to move,
-// resign: the action is None) and act6[i] = action & 63 (destroyed).  Out: the boards in place; legal (nullable; element i at
-// legal[i * legal_stride], so that a kernel can pass its strided global output and keep 64 registers free) = legal moves of
-// the side to move after the step (0 when the game is over); masks: ok = the move was accepted (it flips something: turn + 1),
-// swap = the other player moves next, over = the game ended by this move (winner by count: wb / ww, neither = draw).  An
-// environment with ok = 0 ends with the mover's loss (None, or a move that flips nothing, :49-59).
-RZ_HD void step32_core(u64* black, u64* white, uint32_t btm, uint32_t resign, uint32_t* act6, u64* legal, size_t legal_stride,
-                       uint32_t& ok_out, uint32_t& swap_out, uint32_t& over_out, uint32_t& wb_out, uint32_t& ww_out) {
-    {   // corrupt boards (a stone of each colour on one square: reachable through the reference's acceptance of a move onto an
-        // occupied square that happens to flip something) take the scalar code, see calc_flip32
-        u64 overlap = 0;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) overlap |= black[i] & white[i];
-        if (overlap) {
-            uint32_t ok = 0, swp = 0, over = 0, wb = 0, ww = 0;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {     // unrolled: the arrays stay in registers
-                const uint8_t np = ((btm >> i) & 1u) ? 1 : 2;
-                EnvState st{black[i], white[i], np, 0, 0, 0};
-                const u64 lg = env_step(st, ((resign >> i) & 1u) ? -1 : (int)act6[i]);
-                black[i] = st.black; white[i] = st.white;
-                ok |= (uint32_t)(st.turn == 1) << i;
-                swp |= (uint32_t)(st.next_player != np) << i;
-                over |= (uint32_t)(st.turn == 1 && st.done) << i;
-                wb |= (uint32_t)(st.turn == 1 && st.winner == 1) << i;
-                ww |= (uint32_t)(st.turn == 1 && st.winner == 2) << i;
-                if (legal) legal[i * legal_stride] = lg;
-            }
-            ok_out = ok; swap_out = swp; over_out = over; wb_out = wb; ww_out = ww;
-            return;
-        }
-    }
-    uint32_t A[64], B[64], C[64];
-    uint32_t lo[8], hi[8];
-    transpose32(act6);                        // act6[b]: bit b of the 32 move squares
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        lo[c] = ((c & 1) ? act6[0] : ~act6[0]) & ((c & 2) ? act6[1] : ~act6[1]) & ((c & 4) ? act6[2] : ~act6[2]);
-        hi[c] = ((c & 1) ? act6[3] : ~act6[3]) & ((c & 2) ? act6[4] : ~act6[4]) & ((c & 4) ? act6[5] : ~act6[5]);
-    }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        A[i] = (uint32_t)black[i]; A[32 + i] = (uint32_t)(black[i] >> 32);
-        B[i] = (uint32_t)white[i]; B[32 + i] = (uint32_t)(white[i] >> 32);
-    }
-    transpose32(A); transpose32(A + 32);
-    transpose32(B); transpose32(B + 32);
-#pragma unroll
-    for (int k = 0; k < 64; ++k) {            // A = own (side to move), B = enemy
-        const uint32_t t = (A[k] ^ B[k]) & ~btm;
-        A[k] ^= t; B[k] ^= t;
-    }
-    // flips of the move (reversi_env.py:56, lib/bitboard.py:70-92)
-#pragma unroll
-    for (int k = 0; k < 64; ++k) C[k] = 0;
-    flips_pair<1, 0>(A, B, lo, hi, C);
-    flips_pair<0, 1>(A, B, lo, hi, C);
-    flips_pair<1, 1>(A, B, lo, hi, C);
-    flips_pair<-1, 1>(A, B, lo, hi, C);
-    uint32_t any_flip = 0;
-#pragma unroll
-    for (int k = 0; k < 64; ++k) any_flip |= C[k];
-    const uint32_t ok = any_flip & ~resign;   // a move that flips something: the step goes through (:60-66); else the mover loses
-#pragma unroll
-    for (int k = 0; k < 64; ++k) {            // own ^= flips; own |= move square; enemy ^= flips
-        const uint32_t fl = C[k] & ok;
-        A[k] = (A[k] ^ fl) | (lo[k & 7] & hi[k >> 3] & ok);
-        B[k] ^= fl;
-    }
-    // who moves next (:67-72): the opponent if it has a move, else the mover again, else the game is over
-#pragma unroll
-    for (int k = 0; k < 64; ++k) C[k] = 0;
-    moves_dir<1, 0>(B, A, C); moves_dir<0, 1>(B, A, C); moves_dir<1, 1>(B, A, C); moves_dir<-1, 1>(B, A, C);
-    uint32_t opp_can = 0;
-#pragma unroll
-    for (int k = 0; k < 64; ++k) { C[k] &= ~(A[k] | B[k]); opp_can |= C[k]; }
-    transpose32(C); transpose32(C + 32);
-    if (legal) {                              // provisional: right for every environment whose opponent can move
-#pragma unroll
-        for (int i = 0; i < 32; ++i) legal[i * legal_stride] = (u64)C[i] | ((u64)C[32 + i] << 32);
-    }
-#pragma unroll
-    for (int k = 0; k < 64; ++k) C[k] = 0;
-    moves_dir<1, 0>(A, B, C); moves_dir<0, 1>(A, B, C); moves_dir<1, 1>(A, B, C); moves_dir<-1, 1>(A, B, C);
-    uint32_t me_can = 0;
-#pragma unroll
-    for (int k = 0; k < 64; ++k) { C[k] &= ~(A[k] | B[k]); me_can |= C[k]; }
-    transpose32(C); transpose32(C + 32);      // C[i] / C[32 + i]: the mover's own legal moves per environment
-    // back to black / white
-#pragma unroll
-    for (int k = 0; k < 64; ++k) {
-        const uint32_t t = (A[k] ^ B[k]) & ~btm;
-        A[k] ^= t; B[k] ^= t;
-    }
-    transpose32(A); transpose32(A + 32);
-    transpose32(B); transpose32(B + 32);
-    const uint32_t over = ok & ~opp_can & ~me_can;
-    uint32_t wb = 0, ww = 0;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        const u64 nb = (u64)A[i] | ((u64)A[32 + i] << 32), nw = (u64)B[i] | ((u64)B[32 + i] << 32);
-        black[i] = nb; white[i] = nw;          // unchanged where the move was not accepted (flips and move square were masked with ok)
-        if (legal) {
-            if (!((ok >> i) & 1u) || ((over >> i) & 1u)) legal[i * legal_stride] = 0;
-            else if (!((opp_can >> i) & 1u)) legal[i * legal_stride] = (u64)C[i] | ((u64)C[32 + i] << 32);
-        }
-        if ((over >> i) & 1u) {
-            const uint8_t wn = winner_by_count(nb, nw);
-            wb |= (uint32_t)(wn == 1) << i;
-            ww |= (uint32_t)(wn == 2) << i;
-        }
-    }
-    ok_out = ok; swap_out = ok & opp_can; over_out = over; wb_out = wb; ww_out = ww;
-}
-
-// the same on the byte fields of 32 environments (host twin, tests)
-RZ_HD void step32(u64* black, u64* white, uint8_t* next_player, uint8_t* turn, uint8_t* done, uint8_t* winner, const int8_t* action,
-                  u64* legal, size_t legal_stride) {
-    uint32_t btm = 0, resign = 0, act6[32], ok, swp, over, wb, ww;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        btm |= (uint32_t)(next_player[i] == 1) << i;
-        resign |= (uint32_t)(action[i] < 0) << i;
-        act6[i] = (uint32_t)action[i] & 63u;
-    }
-    step32_core(black, white, btm, resign, act6, legal, legal_stride, ok, swp, over, wb, ww);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        const bool bt = (btm >> i) & 1u;
-        if (!((ok >> i) & 1u)) { winner[i] = bt ? 2 : 1; done[i] = 1; continue; }
-        turn[i] = (uint8_t)(turn[i] + 1);
-        if ((swp >> i) & 1u) next_player[i] = bt ? 2 : 1;
-        if ((over >> i) & 1u) { done[i] = 1; winner[i] = ((wb >> i) & 1u) ? 1 : (((ww >> i) & 1u) ? 2 : 3); }
-    }
 }
 
 }  // namespace bs

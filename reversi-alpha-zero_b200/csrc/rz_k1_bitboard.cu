@@ -67,7 +67,11 @@ __global__ void __launch_bounds__(kThreads, 1) k1_calc_flip_bs(const uint8_t* __
             o[i] = ldg_stream_u64(own + base + i * 32); e[i] = ldg_stream_u64(enemy + base + i * 32);
             ps[i] = __ldg(pos + base + i * 32);
         }
-        bs::calc_flip32(ps, o, e, f);
+        if (bs::any_overlap32(o, e)) {      // see k1_bs_staged
+            for (int i = 0; i < 32; ++i) out[base + i * 32] = calc_flip(pos[base + i * 32] & 63, own[base + i * 32], enemy[base + i * 32]);
+            continue;
+        }
+        bs::calc_flip32<false>(ps, o, e, f);
 #pragma unroll
         for (int i = 0; i < 32; ++i) stg_stream_u64(out + base + i * 32, f[i]);
     }
@@ -117,91 +121,21 @@ __global__ void __launch_bounds__(kThreads, 1) k1_bs_staged(const uint8_t* __res
             o[i] = so[i * 32 + lane]; e[i] = se[i * 32 + lane];
             if (FLIP) ps[i] = sp[i * 32 + lane];
         }
-        __syncwarp();                       // every lane has its copy: the staging buffer may be refilled
+        const size_t ob = t * 1024 + lane;
+        // flips: a thread whose 32 positions include one with a square shared by own and enemy (not a board, but the reference's
+        // arithmetic defines the answer) computes them with the scalar code, straight from the staging buffer
+        const bool scalar_path = FLIP && bs::any_overlap32(o, e);
+        if (scalar_path)
+            for (int i = 0; i < 32; ++i) out[ob + i * 32] = calc_flip(sp[i * 32 + lane] & 63, so[i * 32 + lane], se[i * 32 + lane]);
+        __syncwarp();                       // every lane is done with the staging buffer: it may be refilled
         if (lane == 0 && t + n_warps < n_tiles) {
             tc::fence_proxy_async();
             fetch(t + n_warps);
         }
-        if (FLIP) bs::calc_flip32(ps, o, e, r); else bs::find_correct_moves32(o, e, r);
-        const size_t ob = t * 1024 + lane;
+        if (scalar_path) continue;
+        if (FLIP) bs::calc_flip32<false>(ps, o, e, r); else bs::find_correct_moves32(o, e, r);
 #pragma unroll
         for (int i = 0; i < 32; ++i) stg_stream_u64(out + ob + i * 32, r[i]);
-    }
-}
-
-// fused environment step, bit-sliced (bs::step32), inputs staged like above: black, white (8 KB each per tile) and the
-// next_player / turn / action bytes (1 KB each); done / winner are only ever written.  In place: a warp reads its tile from the
-// staging buffer and writes the tile's new state to global memory; the tile it prefetches meanwhile is a different one.
-constexpr uint32_t kStepStagePerWarp = 2 * 8192 + 3 * 1024;
-constexpr uint32_t kStepStagedSmem = (kThreads / 32) * kStepStagePerWarp + 64 + 128;
-
-__global__ void __launch_bounds__(kThreads, 1) k1_step_bs(u64* __restrict__ black, u64* __restrict__ white, uint8_t* __restrict__ next_player,
-                                                          uint8_t* __restrict__ turn, uint8_t* __restrict__ done, uint8_t* __restrict__ winner,
-                                                          const int8_t* __restrict__ action, u64* __restrict__ legal_out, size_t n_tiles) {
-    extern __shared__ uint8_t k1_smem_raw[];
-    const uint32_t base = (tc::smem_u32(k1_smem_raw) + 127u) & ~127u;
-    uint8_t* sm = k1_smem_raw + (base - tc::smem_u32(k1_smem_raw));
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    const uint32_t bar = base + (kThreads / 32) * kStepStagePerWarp + w * 8;
-    const uint32_t s0 = base + w * kStepStagePerWarp;
-    const u64* sb = reinterpret_cast<const u64*>(sm + w * kStepStagePerWarp);
-    const u64* sw = sb + 1024;
-    const uint8_t* snp = sm + w * kStepStagePerWarp + 16384;
-    const uint8_t* stu = snp + 1024;
-    const int8_t* sac = reinterpret_cast<const int8_t*>(stu + 1024);
-    if (lane == 0) {
-        tc::mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    auto fetch = [&](size_t t) {   // lane 0 only
-        tc::mbar_expect_tx(bar, kStepStagePerWarp);
-        tc::bulk_g2s(s0, black + t * 1024, 8192, bar);
-        tc::bulk_g2s(s0 + 8192, white + t * 1024, 8192, bar);
-        tc::bulk_g2s(s0 + 16384, next_player + t * 1024, 1024, bar);
-        tc::bulk_g2s(s0 + 17408, turn + t * 1024, 1024, bar);
-        tc::bulk_g2s(s0 + 18432, action + t * 1024, 1024, bar);
-    };
-    uint32_t phase = 0;
-    if (warp < n_tiles && lane == 0) fetch(warp);
-    for (size_t t = warp; t < n_tiles; t += n_warps) {
-        u64 b[32], wh[32];
-        uint32_t act6[32], tu4[8], btm = 0, resign = 0;    // byte fields as masks over the 32 environments / packed four per word
-        tc::mbar_wait(bar, phase);
-        phase ^= 1;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) tu4[k] = 0;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            b[i] = sb[i * 32 + lane]; wh[i] = sw[i * 32 + lane];
-            const int a = sac[i * 32 + lane];
-            btm |= (uint32_t)(snp[i * 32 + lane] == 1) << i;
-            resign |= (uint32_t)(a < 0) << i;
-            act6[i] = (uint32_t)a & 63u;
-            tu4[i >> 2] |= (uint32_t)stu[i * 32 + lane] << (8 * (i & 3));
-        }
-        __syncwarp();
-        if (lane == 0 && t + n_warps < n_tiles) {
-            tc::fence_proxy_async();
-            fetch(t + n_warps);
-        }
-        const size_t ob = t * 1024 + lane;
-        uint32_t ok, swp, over, wb, ww;
-        bs::step32_core(b, wh, btm, resign, act6, legal_out ? legal_out + ob : nullptr, 32, ok, swp, over, wb, ww);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const size_t at = ob + i * 32;
-            const bool bt = (btm >> i) & 1u;
-            stg_stream_u64(black + at, b[i]); stg_stream_u64(white + at, wh[i]);
-            if ((ok >> i) & 1u) {
-                turn[at] = (uint8_t)(((tu4[i >> 2] >> (8 * (i & 3))) & 0xffu) + 1u);
-                if ((swp >> i) & 1u) next_player[at] = bt ? 2 : 1;
-                if ((over >> i) & 1u) { done[at] = 1; winner[at] = ((wb >> i) & 1u) ? 1 : (((ww >> i) & 1u) ? 2 : 3); }
-            } else {
-                done[at] = 1; winner[at] = bt ? 2 : 1;   // None or a move that flips nothing: the mover loses
-            }
-        }
     }
 }
 
@@ -219,7 +153,6 @@ static int k1_staged_attr() {
     if (!done) {
         RZ_CUDA_TRY(cudaFuncSetAttribute(k1_bs_staged<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedSmem));
         RZ_CUDA_TRY(cudaFuncSetAttribute(k1_bs_staged<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedSmem));
-        RZ_CUDA_TRY(cudaFuncSetAttribute(k1_step_bs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStepStagedSmem));
         done = true;
     }
     return RZ_OK;
@@ -363,17 +296,6 @@ int rz_step_dev(uint64_t* black, uint64_t* white, uint8_t* next_player, uint8_t*
                 const int8_t* action, uint64_t* legal_out, size_t n, void* stream) {
     RZ_REQUIRE(n == 0 || (black && white && next_player && turn && done && winner && action), "rz_step_dev: null pointer");
     if (n == 0) return RZ_OK;
-    if (k1_impl() != 0 && n >= 1024 && aligned16(black) && aligned16(white) && aligned16(next_player) && aligned16(turn) && aligned16(action)) {
-        const size_t tiles = n / 1024;
-        RZ_TRY(k1_staged_attr());
-        k1_step_bs<<<grid_for_tiles(tiles), kThreads, kStepStagedSmem, (cudaStream_t)stream>>>(black, white, next_player, turn, done, winner, action,
-                                                                                              legal_out, tiles);
-        RZ_LAUNCH_CHECK();
-        const size_t d = tiles * 1024;
-        black += d; white += d; next_player += d; turn += d; done += d; winner += d; action += d; n -= d;
-        if (legal_out) legal_out += d;
-        if (n == 0) return RZ_OK;
-    }
     k1_step<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(black, white, next_player, turn, done, winner, action, legal_out, n);
     RZ_LAUNCH_CHECK();
     return RZ_OK;
@@ -449,28 +371,6 @@ int rz_step(uint64_t* black, uint64_t* white, uint8_t* next_player, uint8_t* tur
 // ---- scalar host twins (single-environment Python objects) ---------------------------------------
 uint64_t rz_find_correct_moves_host(uint64_t own, uint64_t enemy) { return find_correct_moves(own, enemy); }
 uint64_t rz_calc_flip_host(int pos, uint64_t own, uint64_t enemy) { return calc_flip(pos & 63, own, enemy); }
-
-int rz_step_bitsliced_host(uint64_t* black, uint64_t* white, uint8_t* next_player, uint8_t* turn, uint8_t* done, uint8_t* winner,
-                           const int8_t* action, uint64_t* legal_out, size_t n) {
-    RZ_REQUIRE(n == 0 || (black && white && next_player && turn && done && winner && action), "rz_step_bitsliced_host: null pointer");
-    for (size_t at = 0; at < n; at += 32) {
-        u64 b[32], w[32], lg[32];
-        uint8_t np[32], tu[32], dn[32], wi[32];
-        int8_t ac[32];
-        const size_t m = n - at < 32 ? n - at : 32;
-        for (size_t i = 0; i < 32; ++i) {
-            const size_t j = i < m ? at + i : at;   // pad with a copy of the group's first environment
-            b[i] = black[j]; w[i] = white[j]; np[i] = next_player[j]; tu[i] = turn[j]; dn[i] = done[j]; wi[i] = winner[j]; ac[i] = action[j];
-        }
-        bs::step32(b, w, np, tu, dn, wi, ac, lg, 1);
-        for (size_t i = 0; i < m; ++i) {
-            black[at + i] = b[i]; white[at + i] = w[i]; next_player[at + i] = np[i]; turn[at + i] = tu[i]; done[at + i] = dn[i];
-            winner[at + i] = wi[i];
-            if (legal_out) legal_out[at + i] = lg[i];
-        }
-    }
-    return RZ_OK;
-}
 
 // host twins of the bit-sliced operators (the same header compiled for the host, groups of 32 consecutive positions): they let
 // the CPU test suite hold the formulation the GPU kernels use against the oracle.  pos may be NULL for the legal-move variant.

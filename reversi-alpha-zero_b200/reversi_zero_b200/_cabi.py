@@ -66,7 +66,6 @@ SIGNATURES = {
     "rz_last_error": (C.c_char_p, []),
     "rz_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "rz_bitsliced_host": (C.c_int, [u8p, u64p, u64p, u64p, sz]),
-    "rz_step_bitsliced_host": (C.c_int, [u64p, u64p, u8p, u8p, u8p, u8p, i8p, u64p, sz]),
     "rz_find_correct_moves_dev": (C.c_int, [vp, vp, vp, sz, vp]),
     "rz_find_correct_moves": (C.c_int, [u64p, u64p, u64p, sz]),
     "rz_calc_flip_dev": (C.c_int, [vp, vp, vp, vp, sz, vp]),

@@ -113,17 +113,6 @@ def bitsliced_host(own, enemy, pos=None):
     return out
 
 
-def step_bitsliced_host(black, white, next_player, turn, done, winner, action, want_legal=False):
-    """Host twin of the bit-sliced fused step the GPU kernel runs (rz_step_bitsliced_host); in place like step_batch.  For tests."""
-    n = black.size
-    legal = np.empty(n, dtype=np.uint64) if want_legal else None
-    p = lambda a, t: a.ctypes.data_as(t)
-    _cabi.check(_cabi.lib().rz_step_bitsliced_host(p(black, _cabi.u64p), p(white, _cabi.u64p), p(next_player, _cabi.u8p), p(turn, _cabi.u8p),
-                                                    p(done, _cabi.u8p), p(winner, _cabi.u8p), p(action, _cabi.i8p),
-                                                    p(legal, _cabi.u64p) if want_legal else None, n), "rz_step_bitsliced_host")
-    return legal
-
-
 def dihedral_batch(x, t, device="cuda:0"):
     """rz_dihedral_dev over arrays: out[i] = flip_vertical if t[i] & 4, then (t[i] & 3) x rotate90 of x[i]
     (lib/bitboard.py:119-159 in the order of agent/player.py:166-179,300-305) -- the device code the engine's leaf
