@@ -147,33 +147,38 @@ def cpu_baseline(budget_s, processes=None, torch_threads=1):
 
 def run_reference(args):
     """CPU port of the reference's self-play worker, one game stream per usable host core
-    (worker/self_play.py:36-41); each step is a time-bounded sample of the same workload."""
+    (worker/self_play.py:36-41), started once; each step is one time-bounded window of that run (the streams play
+    games back to back from the opening), W untimed windows first, then K timed ones -- the whole run is bounded to
+    about three minutes, so a step is min(12, 180 / (K + W)) seconds."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import selfplay_cpu
     cores = selfplay_cpu.usable_cores()
-    budget = 12.0
-    vals = []
-    for i in range(args.warmup + args.steps):
-        r, gps = cpu_baseline(budget_s=budget, processes=cores)
-        if i >= args.warmup:
-            vals.append((gps, r))
-    gps = sum(v for v, _ in vals) / len(vals)
-    eps = sum(r["expansions_per_s"] for _, r in vals) / len(vals)
+    n_win = args.warmup + args.steps
+    total_s = float(os.environ.get("RZ_BENCH_REFERENCE_TOTAL_S", "180"))   # the tests shorten it
+    window_s = max(0.5, min(12.0, total_s / n_win))
+    wins, tot = selfplay_cpu.measure_windows({k: v for k, v in MODEL_KW.items()}, dict(PLAY_KW), windows=n_win, window_s=window_s,
+                                             processes=cores)
+    timed = wins[args.warmup:]
+    eps = sum(w["expansions_per_s"] for w in timed) / len(timed)
     epg, epg_src = expansions_per_game()
-    sample = (f"each step: {cores} processes x {budget:.0f} s of one game each from the opening (400 sims/move), torch fp32 CPU forward, "
-              f"1 thread/process; games/s = expansions/s / {epg:.0f} expansions per complete game ({epg_src})")
+    gps = eps / epg
+    sample = (f"{cores} processes started once, games played back to back from the opening ({args.sims} sims/move), torch fp32 CPU forward, "
+              f"1 thread/process; {args.warmup} untimed + {args.steps} timed windows of {window_s:.1f} s; {sum(w['expansions'] for w in timed)} "
+              f"expansions in the timed windows; games/s = expansions/s / {epg:.0f} expansions per complete game ({epg_src})")
     line = dict(impl="reference", metric="self_play_games_per_sec", value=gps, unit="games/s", n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=budget * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                data="synthetic", config=workload_config(args, cores=cores), node_expansions_per_sec=eps,
+                warmup=args.warmup, ms_per_step=window_s * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic (random-init ch5 weights, self-generated games)", config=workload_config(args), node_expansions_per_sec=eps,
                 cpu_baseline=dict(value=gps, unit="games/s", cores=cores, kind="port", sample=sample, value_per_core=gps / max(1, cores),
-                                  port_vs_unmodified_reference=port_calibration()),
+                                  mean_nn_batch=sum(w["mean_batch"] for w in timed) / len(timed), plies_decided=tot["plies"],
+                                  games_finished=tot["games_finished"], port_vs_unmodified_reference=port_calibration()),
                 e2e=dict(value=gps, unit="games/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     _emit(json.dumps(line))
 
 
-def workload_config(args, **extra):
+def workload_config(args):
+    """the workload both arms are measured on (identical in the `--impl reference` line)"""
     c = dict(workload="selfplay ch5 net (256x10, random-init) G=%d games/GPU sims=%d K=8 c_puct=5 vl=3 noise=0.25 tau_turn=4 "
                       "thinking_loop=1 solver=%s resign=off" % (args.games, args.sims, "on(50/50)" if PLAY_KW.get("use_solver_turn") else "off"),
              games_per_gpu=args.games, simulation_num_per_move=PLAY_KW["simulation_num_per_move"],
@@ -181,7 +186,6 @@ def workload_config(args, **extra):
              step="one step = simulation_num_per_move / parallel_search_num waves (every resident game decides about one move); "
                   "one wave = MCTS tick kernel + tcgen05 tower launch over the leaf batch",
              arithmetic="network: f16 operands, f32 accumulate + f32 residual stream; MCTS: f32 W, f64 PUCT as numpy promotes; rules: u64", parallelism=f"dp{args.gpus} (games sharded by rank)")
-    c.update(extra)
     return c
 
 
@@ -204,12 +208,10 @@ def main():
     PLAY_KW["simulation_num_per_move"] = args.sims
     if args.solver:  # ch5.yml's default solver settings instead of the benchmark configuration (solver off)
         PLAY_KW["use_solver_turn"] = PLAY_KW["use_solver_turn_in_simulation"] = 50
-    if args.impl == "reference":
-        if args.steps > 4:
-            args.steps, args.warmup = 2, 0  # each step is a 12 s time-bounded CPU sample (+ process start-up)
-        return run_reference(args)
     if args.warmup < 3:
         args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
 
     import numpy as np
     import torch
@@ -441,14 +443,15 @@ def main():
     line = dict(metric="self_play_games_per_sec", value=value, unit="games/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=run_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16",
                 data="synthetic (random-init ch5 weights, self-generated games)",
-                config=workload_config(args, waves_per_step=wps, hbm_in_use_gb_rank0=hbm_used_gb, games_finished_in_window=games,
-                                       games_finished_in_warmup_rank0=s0["games_finished"], waves_in_warmup=args.warmup * wps,
-                                       value_definition="games finished inside the timed window / device time of the window",
-                                       value_renewal_estimate=value_est, measured_over_estimate=value / value_est if value_est else None,
-                                       plies_decided=plies, plies_per_sec_over_60=plies / secs / PLIES_PER_GAME,
-                                       expansions_per_game=epg, expansions_per_game_source=epg_src,
-                                       warm_start=profile_src,
-                                       timing="CUDA events on the engine streams, first to last wave; max over ranks"),
+                config=workload_config(args),
+                window=dict(waves_per_step=wps, hbm_in_use_gb_rank0=hbm_used_gb, games_finished_in_window=games,
+                            games_finished_in_warmup_rank0=s0["games_finished"], waves_in_warmup=args.warmup * wps,
+                            value_definition="games finished inside the timed window / device time of the window",
+                            value_renewal_estimate=value_est, measured_over_estimate=value / value_est if value_est else None,
+                            plies_decided=plies, plies_per_sec_over_60=plies / secs / PLIES_PER_GAME,
+                            expansions_per_game=epg, expansions_per_game_source=epg_src,
+                            warm_start=profile_src,
+                            timing="CUDA events on the engine streams, first to last wave; max over ranks"),
                 node_expansions_per_sec=exp_per_s, simulations_per_sec=sims / secs,
                 roofline=roofline, cpu_baseline=cb, clocks=clocks,
                 e2e=dict(value=e2e_value, unit="games/s", h2d_bytes_per_step=int(n_blob * 4 / args.steps), d2h_bytes_per_step=int(d2h / args.steps),

@@ -490,6 +490,8 @@ class SelfPlayWorker:
             return
         rc = self.config.resource
         game_id = datetime.now().strftime("%Y%m%d-%H%M%S.%f")
+        if self.world_size > 1:   # ranks share the directory: same suffix rule as the play_data files
+            game_id += f"_r{self.rank}"
         path = os.path.join(rc.self_play_ggf_data_dir, rc.ggf_filename_tmpl % game_id)
         with open(path, "wt") as f:
             for line in self.ggf_lines:
