@@ -42,3 +42,17 @@ def test_reference_arm_line_and_shared_config():
     assert d["value"] > 0 and d["e2e"] == dict(value=d["value"], unit="games/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "windows" in cb["sample"]
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+    """the driver launches the reference arm like the B200 arm (torchrun, one rank per GPU): rank 0 alone measures and prints,
+    the other ranks exit 0 without work"""
+    env = dict(os.environ, RZ_BENCH_REFERENCE_TOTAL_S="6", CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "3",
+                        "--warmup", "3"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [x for x in r.stdout.splitlines() if x.strip().startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["config"]["parallelism"].startswith("dp2")
