@@ -17,8 +17,9 @@ count through the public worker (host weights -> device, SelfPlayWorker.start() 
 play_*.json + GGF files on disk) over wall-clock time.
 
 `other_baseline_configs` (rank 0, outside every timed region): BASELINE config 5 (legal-move / flip / step operators on
-10 M positions, GB/s vs the measured HBM peak) and config 4 (the same tower kernel on a 19-block network), so that they
-appear in the same driver-run record as the headline.
+10 M positions, GB/s vs the measured HBM peak), config 4 (the same tower kernel on a 19-block network) and the trainer-side
+ingest of SURVEY 8(f).4 (tools/ingest_bench.py in its own process), so that they appear in the same driver-run record as the
+headline.
 
 Launch: python bench.py [--gpus N --steps K --warmup W] (N > 1 under torch.distributed.run, one rank per
 GPU).  `--impl reference` times the CPU port of the reference's own self-play worker (oracle/) on the host
@@ -428,6 +429,15 @@ def main():
                                                   frac_of_sustained_peak=r4["frac_of_sustained_peak"])
         except Exception as ex:
             extra["config4_19block_tower"] = dict(error=repr(ex))
+        try:    # SURVEY 8(f).4, trainer-side ingest: 1 M play rows -> 8.4 M training records (tools/ingest_bench.py, own process)
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ingest_bench.py")], stdout=subprocess.PIPE,
+                                 stderr=subprocess.PIPE, text=True, timeout=240)   # rank 0 = local device 0 = the tool's cuda:0
+            r8 = json.loads(out.stdout.strip().splitlines()[-1])
+            extra["trainer_ingest_1M_rows"] = {k: r8[k] for k in ("rows", "records", "bytes_per_row", "kernel_ms", "gbs", "frac_of_measured_hbm",
+                                                                  "records_per_s", "from_file_records_per_s")}
+            extra["trainer_ingest_1M_rows"]["cpu_reference_loader_records_per_s"] = r8["cpu_baseline"]["records_per_s"]
+        except Exception as ex:
+            extra["trainer_ingest_1M_rows"] = dict(error=repr(ex))
 
     cb = None
     if not args.no_cpu_baseline:
