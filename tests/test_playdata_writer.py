@@ -108,3 +108,18 @@ def test_ply_without_visits_does_not_crash(tmp_path):
         pol = list(np.zeros(64) / np.zeros(64).sum())
     want = json.dumps([[[int(ob.dihedral(P[0].own, t)), int(ob.dihedral(P[0].enemy, t))], pol, -1] for t in range(8)])
     assert open(path).read() == want and "NaN" in want
+
+
+def test_writer_bench_tool_on_complete_games():
+    """tools/writer_bench.py (capacity of one writer thread on complete games, profiles/writer_bench_r02.json): the stand-in
+    engine's games go through the unmodified harvest loop; no timing assertion -- only that the workload is what it says
+    (complete games, ~60 recorded plies, 8 records per ply, draws dropped with ch5's rate, a few hundred KB of JSON per game)"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import writer_bench
+    r = writer_bench.run(total=40, pool=16)
+    assert r["games"] == 40 and 55 <= r["plies_per_game"] <= 60
+    assert 1 <= r["files_written"] <= 40 and 100e3 < r["bytes_per_written_game"] < 400e3
+    c = r["c_writer_alone"]
+    assert c["games"] == 16 and c["records"] == 8 * round(r["plies_per_game"] * 16)
